@@ -1,0 +1,134 @@
+"""Generates tests/golden/*.pt by running the UNMODIFIED reference (imported from /root/reference,
+build container only). Run:  python tests/gen_golden.py
+The fixtures pin both the oracle (oracle/render_ref.py) and the CUDA path; they carry every input,
+the reference's CPU-generator draws, its outputs and — for the training case — its autograd gradients.
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+import refharness as rh  # noqa: E402
+from oracle import render_ref as R  # noqa: E402
+
+OUT = os.path.join(HERE, "golden")
+
+
+def make_networks(mods, opt, seed, perturb=0.02):
+    torch.manual_seed(seed)
+    sdf = mods.implicit.SDFNetwork(opt)
+    rgb = mods.implicit.RGBNetwork(opt)
+    ren = mods.renderer.Renderer(opt, sdf, rgb)
+    with torch.no_grad():   # geometric init zeroes the latent columns: perturb so every weight matters
+        for p in sdf.parameters():
+            p.add_(perturb * torch.randn_like(p))
+    return sdf, rgb, ren
+
+
+def random_camera(mods, opt, B):
+    az = torch.rand(B) * 6.2831853
+    el = (torch.rand(B) - 0.5)
+    th = (torch.rand(B) - 0.5) * 0.3
+
+    def trig(a):
+        return torch.stack([a.cos(), a.sin()], -1)
+    Ry = mods.camera.azim_to_rotation_matrix(trig(az), "trig")
+    Rx = mods.camera.elev_to_rotation_matrix(trig(el), "trig")
+    Rz = mods.camera.roll_to_rotation_matrix(trig(th), "trig")
+    P = torch.tensor([[-1, 0, 0], [0, 0, -1], [0, -1, 0]]).float()
+    Rm = Rz @ Rx @ Ry @ P
+    sd = 1 + 0.1 * (torch.rand(B) - 0.5)
+    t = torch.stack([torch.zeros(B), torch.zeros(B), sd * opt.camera.dist], -1)
+    pose = torch.cat([Rm, t[..., None]], -1)
+    intr = mods.camera.get_intr(opt, 1 + 0.05 * (torch.rand(B) - 0.5))
+    return pose, intr, sd
+
+
+def case_render(mods, name, H, W, B, n_rays, training, seed):
+    opt = rh.load_reference_opt(H=H, W=W)
+    sdf, rgb, ren = make_networks(mods, opt, seed)
+    pose, intr, sd = random_camera(mods, opt, B)
+    zs, zr = torch.randn(B, 64) * 0.3, torch.randn(B, 64) * 0.3
+    ray_idx = None
+    if n_rays is not None:
+        ray_idx = torch.stack([torch.randperm(H * W)[:n_rays] for _ in range(B)])
+    Rn = n_rays if n_rays is not None else H * W
+    S = opt.render.n_samples_uniform
+    leaves = dict(pose=pose, intr=intr, scale_dist=sd, z_sdf=zs, z_rgb=zr)
+    for v in leaves.values():
+        v.requires_grad_(training)
+    torch.manual_seed(seed + 100)
+    state = torch.get_rng_state()
+    outs = ren(opt, pose, intr, sd, zs, zr, ray_idx=ray_idx, training=training)
+    torch.set_rng_state(state)
+    u, eik_idx, eik_pts = R.draw_render_rng(B * Rn, S, training)
+    names = ["rgb", "mask", "mask_hard", "depth", "normal", "grad_eik"]
+    fx = dict(H=H, W=W, B=B, S=S, training=training, ray_idx=ray_idx,
+              sdf_params={k: v.detach().clone() for k, v in sdf.state_dict().items()},
+              rgb_params={k: v.detach().clone() for k, v in rgb.state_dict().items()},
+              beta=ren.density.beta.detach().clone(),
+              inputs={k: v.detach().clone() for k, v in leaves.items()},
+              rng=dict(u=u, eik_idx=eik_idx, eik_pts=eik_pts),
+              outputs={n: (o.detach().clone() if o is not None else None) for n, o in zip(names, outs)})
+    if training:
+        # fixed cotangents -> one scalar -> the reference's autograd gradients
+        torch.manual_seed(seed + 200)
+        cot = {n: torch.randn_like(o) for n, o in zip(names, outs) if o is not None and n != "mask_hard"}
+        scalar = sum((cot[n] * o).sum() for n, o in zip(names, outs) if n in cot)
+        params = dict(ren.named_parameters())   # density.beta + sdf_network.* + rgb_network.*
+        wrt = list(params.values()) + list(leaves.values())
+        grads = torch.autograd.grad(scalar, wrt, allow_unused=True)
+        keys = list(params.keys()) + list(leaves.keys())
+        fx["cotangents"] = cot
+        fx["grads"] = {k: (g.detach().clone() if g is not None else None) for k, g in zip(keys, grads)}
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print("wrote", name, {n: (tuple(o.shape) if o is not None else None) for n, o in fx["outputs"].items()})
+
+
+def case_sdf_query(mods, name, seed):
+    opt = rh.load_reference_opt()
+    sdf, _, _ = make_networks(mods, opt, seed)
+    B, N = 3, 50
+    pts = (torch.rand(B * N, 3) - 0.5) * 1.6
+    z = torch.randn(B, 64) * 0.3
+    s, f, g = sdf.get_conditional_output(opt, B, pts.clone(), z, compute_grad=True)
+    torch.save(dict(sdf_params={k: v.detach().clone() for k, v in sdf.state_dict().items()},
+                    pts=pts, z_sdf=z, B=B, sdf=s.detach(), feat=f.detach(), grad=g.detach()),
+               os.path.join(OUT, name + ".pt"))
+    print("wrote", name)
+
+
+def case_losses(mods, name, seed):
+    opt = rh.load_reference_opt()
+    L = mods.loss.Loss(opt)
+    torch.manual_seed(seed)
+    B, Rn = 2, 300
+    rgb, rgb_gt = torch.rand(B, Rn, 3), torch.rand(B, Rn, 3)
+    mask, mask_gt = torch.rand(B, Rn, 1), (torch.rand(B, Rn, 1) > 0.4).float()
+    n = torch.nn.functional.normalize(torch.randn(B, Rn, 3), dim=-1)
+    n_gt = torch.nn.functional.normalize(n + 0.3 * torch.randn(B, Rn, 3), dim=-1)
+    eik = 1 + 0.1 * torch.randn(B * 2 * Rn)
+    valid = (mask_gt > 0.5) & (mask > 0.5)
+    out = dict(render=L.MSE_loss(rgb, rgb_gt), mask=L.mask_loss(mask, mask_gt),
+               normal=L.normal_loss(n, n_gt, valid, tolerance=opt.reg.normal_tol),
+               eikonal=L.MSE_loss(eik.view(B, -1), 1))
+    torch.save(dict(rgb=rgb, rgb_gt=rgb_gt, mask=mask, mask_gt=mask_gt, normal=n, normal_gt=n_gt, grad_eik=eik,
+                    B=B, losses=out), os.path.join(OUT, name + ".pt"))
+    print("wrote", name, {k: float(v) for k, v in out.items()})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    mods = rh.import_reference()
+    case_render(mods, "render_eval_12x12", 12, 12, 2, None, False, seed=1)
+    case_render(mods, "render_train_40rays", 16, 16, 2, 40, True, seed=2)
+    case_render(mods, "render_train_full_8x8", 8, 8, 1, None, True, seed=3)
+    case_sdf_query(mods, "sdf_query", seed=4)
+    case_losses(mods, "losses", seed=5)
+
+
+if __name__ == "__main__":
+    main()
