@@ -1,0 +1,108 @@
+"""GPU parity for chamfer_3D.forward/backward through the C ABI: bit-exact dist + idx against the C oracle
+and (when oracle/_ref was built) against the UNMODIFIED reference kernel recompiled for sm_100a."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import chamfer_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(a, b):
+    from shapeclipper_b200 import chamfer_3D
+    B, N, M = a.shape[0], a.shape[1], b.shape[1]
+    d1 = torch.zeros(B, N, device="cuda"); d2 = torch.zeros(B, M, device="cuda")
+    i1 = torch.zeros(B, N, dtype=torch.int32, device="cuda"); i2 = torch.zeros(B, M, dtype=torch.int32, device="cuda")
+    assert chamfer_3D.forward(a, b, d1, d2, i1, i2) == 1
+    return d1, d2, i1, i2
+
+
+def _bits(t):
+    return t.detach().cpu().numpy().view(np.int32)
+
+
+@pytest.mark.parametrize("B,N,M", [(1, 1, 1), (1, 5, 3), (2, 513, 1025), (3, 1000, 777), (1, 4099, 2048),
+                                   (1, 20000, 6001), (16, 300, 300)])
+def test_forward_bit_exact_vs_oracle(B, N, M):
+    g = torch.Generator().manual_seed(B * 1000003 + N * 101 + M)
+    a = torch.randn(B, N, 3, generator=g)
+    b = torch.randn(B, M, 3, generator=g) * 0.7 + 0.1
+    e1, e2, j1, j2 = chamfer_ref.chamfer_forward(a.numpy(), b.numpy())
+    d1, d2, i1, i2 = _run(a.cuda(), b.cuda())
+    assert (_bits(d1) == e1.view(np.int32)).all() and (_bits(d2) == e2.view(np.int32)).all()
+    assert (i1.cpu().numpy() == j1).all() and (i2.cpu().numpy() == j2).all()
+
+
+def test_ties_resolve_to_lowest_index():
+    g = torch.Generator().manual_seed(7)
+    b = torch.randn(1, 9000, 3, generator=g)
+    b[0, 8000] = b[0, 40]; b[0, 4100] = b[0, 40]; b[0, 41] = b[0, 40]
+    a = b[:, 40:41].clone() + 1e-3
+    a = torch.cat([a, b[:, :100]], 1)
+    e1, e2, j1, j2 = chamfer_ref.chamfer_forward(a.numpy(), b.numpy())
+    d1, d2, i1, i2 = _run(a.cuda(), b.cuda())
+    assert i1[0, 0].item() == 40 == j1[0, 0]
+    assert (i1.cpu().numpy() == j1).all() and (i2.cpu().numpy() == j2).all()
+    assert (_bits(d1) == e1.view(np.int32)).all()
+
+
+def test_quantised_clouds_many_ties():
+    g = torch.Generator().manual_seed(11)
+    a = torch.randint(-6, 6, (2, 3000, 3), generator=g).float() / 4
+    b = torch.randint(-6, 6, (2, 2500, 3), generator=g).float() / 4
+    e1, e2, j1, j2 = chamfer_ref.chamfer_forward(a.numpy(), b.numpy())
+    d1, d2, i1, i2 = _run(a.cuda(), b.cuda())
+    assert (i1.cpu().numpy() == j1).all() and (i2.cpu().numpy() == j2).all()
+    assert (_bits(d1) == e1.view(np.int32)).all() and (_bits(d2) == e2.view(np.int32)).all()
+
+
+def test_self_distance_full_size():
+    # size-independent property at BASELINE.json's eval size: cloud vs itself -> dist 0, idx = arange
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(1, 100000, 3, generator=g).cuda()
+    d1, d2, i1, i2 = _run(a, a.clone())
+    ar = torch.arange(100000, dtype=torch.int32, device="cuda")[None]
+    assert (d1 == 0).all() and (d2 == 0).all() and (i1 == ar).all() and (i2 == ar).all()
+
+
+def test_matches_unmodified_reference_kernel():
+    from oracle import build_ref
+    ref = build_ref.load()
+    if ref is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference in the build container)")
+    g = torch.Generator().manual_seed(5)
+    for (B, N, M) in [(1, 30000, 25000), (4, 2048, 3000), (2, 700, 513)]:
+        a = torch.randn(B, N, 3, generator=g).cuda()
+        b = (torch.randn(B, M, 3, generator=g) * 0.8).cuda()
+        r = [torch.zeros(B, N, device="cuda"), torch.zeros(B, M, device="cuda"),
+             torch.zeros(B, N, dtype=torch.int32, device="cuda"), torch.zeros(B, M, dtype=torch.int32, device="cuda")]
+        assert ref.forward(a, b, *r) == 1
+        torch.cuda.synchronize()
+        d1, d2, i1, i2 = _run(a, b)
+        assert (_bits(d1) == _bits(r[0])).all() and (_bits(d2) == _bits(r[1])).all()
+        assert (i1 == r[2]).all() and (i2 == r[3]).all()
+
+
+def test_backward_vs_oracle():
+    from shapeclipper_b200 import chamfer_3D
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(2, 600, 3, generator=g); b = torch.randn(2, 450, 3, generator=g)
+    e1, e2, j1, j2 = chamfer_ref.chamfer_forward(a.numpy(), b.numpy())
+    g1 = torch.randn(2, 600, generator=g); g2 = torch.randn(2, 450, generator=g)
+    ea, eb = chamfer_ref.chamfer_backward(a.numpy(), b.numpy(), g1.numpy(), g2.numpy(), j1, j2)
+    ga = torch.zeros(2, 600, 3, device="cuda"); gb = torch.zeros(2, 450, 3, device="cuda")
+    ok = chamfer_3D.backward(a.cuda(), b.cuda(), ga, gb, g1.cuda(), g2.cuda(),
+                             torch.from_numpy(j1).cuda(), torch.from_numpy(j2).cuda())
+    assert ok == 1
+    # float atomics: summation order differs -> tolerance
+    assert np.allclose(ga.cpu().numpy(), ea, rtol=1e-5, atol=1e-5)
+    assert np.allclose(gb.cpu().numpy(), eb, rtol=1e-5, atol=1e-5)
+
+
+def test_requires_cuda_tensors():
+    from shapeclipper_b200 import chamfer_3D, _lib
+    a = torch.randn(1, 4, 3)
+    with pytest.raises(_lib.NativeLibraryError):
+        chamfer_3D.forward(a, a, torch.zeros(1, 4), torch.zeros(1, 4),
+                           torch.zeros(1, 4, dtype=torch.int32), torch.zeros(1, 4, dtype=torch.int32))
