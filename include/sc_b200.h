@@ -8,7 +8,7 @@
  * Reference interfaces replaced (paths relative to the reference tree):
  *   sc_chamfer_forward   external/chamfer3D/chamfer_cuda.cpp:17-19  chamfer_forward  -> chamfer3D.cu:137-154
  *   sc_chamfer_backward  external/chamfer3D/chamfer_cuda.cpp:22-26  chamfer_backward -> chamfer3D.cu:176-195
- * (render / SDF-query / CLIP entry points are appended below as they land.)
+ *   sc_render_*          model/renderer.py:57 Renderer.forward, model/implicit.py:163 get_conditional_output
  */
 #ifndef SC_B200_H_
 #define SC_B200_H_
@@ -42,6 +42,73 @@ int sc_chamfer_backward(const float* xyz1, const float* xyz2, int batch, int n, 
                         const float* graddist1, const float* graddist2,
                         const int32_t* idx1, const int32_t* idx2,
                         float* gradxyz1, float* gradxyz2, cudaStream_t stream);
+
+/* ---- fused SDF/RGB-MLP volume renderer ----------------------------------
+ * Replaces model/renderer.py:57-209 (Renderer.forward), model/implicit.py:138-239 (SDFNetwork.forward,
+ * get_conditional_output, RGBNetwork.forward, LaplaceDensity) and the slice loop of utils/eval_3D.py:21-38.
+ *
+ * Weights travel as one packed blob (sc_render_pack_weights) built from the nn.Linear tensors of
+ * sdf_network.lin0..5 / rgb_network.lin0..3 ([out,in] row-major fp32, the checkpoint layout).
+ * Per-image latent biases cb [B][4][64] come from sc_render_latent_bias (z_sdf, z_rgb are [B,64]).
+ * scratch: sc_render_scratch_bytes(backward) bytes of device memory private to one call in flight. */
+typedef struct ScRenderArgs {
+    int mode;               /* 0 = rays (Renderer.forward), 1 = points (SDFNetwork.get_conditional_output) */
+    int batch;              /* B */
+    int n_per_image;        /* rays per image R (mode 0) / points per image N (mode 1) */
+    int n_samples;          /* S samples per ray (mode 0): 4 | S, S | 128 */
+    int want_grad;          /* mode 1: also produce d sdf / d point */
+    int want_feat;          /* mode 1: also produce the 64 SDF features */
+    int detach_latent;      /* backward, mode 1: latent bias adjoints do not reach z_sdf (compute_grad=True path) */
+    float beta_min;         /* LaplaceDensity beta_min (1e-4) */
+    float cam_dist;         /* opt.camera.dist */
+    float half_range;       /* 0.7 */
+    float bg_color;         /* opt.data.bgcolor */
+    float normal_pow;       /* opt.reg.normal_pow */
+    const float* blob;      /* packed weights, sc_render_blob_floats() floats */
+    const float* cb;        /* [B][4][64] */
+    const float* beta_param;/* device scalar: renderer.density.beta */
+    /* mode 0 inputs */
+    const float* cam_loc;   /* [B,3] */
+    const float* ray_dirs;  /* [B,R,3] unit */
+    const float* depth_fac; /* [B,R] */
+    const float* scale_dist;/* [B] */
+    const float* t_vals;    /* [S] linspace(0,1,S) */
+    const float* jitter;    /* [B*R,S] stratified u in [0,1) or NULL (bin edges) */
+    /* mode 1 input */
+    const float* points;    /* [B,N,3] */
+    /* forward outputs (mode 0) */
+    float* rgb;             /* [B,R,3] */
+    float* mask;            /* [B,R] */
+    float* mask_hard;       /* [B,R] */
+    float* depth;           /* [B,R] */
+    float* normal;          /* [B,R,3] */
+    /* forward outputs (mode 1) */
+    float* sdf;             /* [B,N] */
+    float* feat;            /* [B,N,64] or NULL */
+    float* grad;            /* [B,N,3] or NULL */
+    /* backward inputs: adjoints of the outputs above (NULL = zero) */
+    const float* rgb_bar; const float* mask_bar; const float* depth_bar; const float* normal_bar;
+    const float* sdf_bar; const float* grad_bar;
+    /* backward outputs */
+    float* grad_partial;    /* [n_ctas][sc_render_grad_floats()] per-CTA folded weight-gradient partials (zeroed by callee) */
+    float* cb_bar;          /* [B][7][64] per-image bias adjoints (zeroed by caller) */
+    float* ray_dirs_bar;    /* [B,R,3] */
+    float* depth_fac_bar;   /* [B,R] */
+    float* cam_loc_bar;     /* [B,3]  (zeroed by caller; atomics) */
+    float* scale_dist_bar;  /* [B]    (zeroed by caller; atomics) */
+    float* points_bar;      /* [B,N,3] (mode 1) */
+    void* scratch;          /* sc_render_scratch_bytes() */
+} ScRenderArgs;
+
+size_t sc_render_blob_floats(void);
+size_t sc_render_grad_floats(void);
+int sc_render_num_ctas(void);                      /* persistent grid = SM count of the current device */
+size_t sc_render_scratch_bytes(int backward);
+/* w/b: arrays of 10 device pointers: sdf lin0..5 then rgb lin0..3 (weights [out,in], biases [out]) */
+int sc_render_pack_weights(const float* const* w, const float* const* b, float* blob, cudaStream_t stream);
+int sc_render_latent_bias(const float* blob, const float* z_sdf, const float* z_rgb, int batch, float* cb,
+                          cudaStream_t stream);
+int sc_render_forward(const ScRenderArgs* args, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

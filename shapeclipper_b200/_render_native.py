@@ -1,0 +1,104 @@
+"""ctypes mirror of ScRenderArgs (include/sc_b200.h) and thin launch helpers. Device pointers only; every
+launch goes to the current torch stream of the tensors' device. No fallback: errors raise."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_fp = ctypes.c_void_p
+
+
+class ScRenderArgs(ctypes.Structure):
+    _fields_ = [
+        ("mode", ctypes.c_int), ("batch", ctypes.c_int), ("n_per_image", ctypes.c_int), ("n_samples", ctypes.c_int),
+        ("want_grad", ctypes.c_int), ("want_feat", ctypes.c_int), ("detach_latent", ctypes.c_int),
+        ("beta_min", ctypes.c_float), ("cam_dist", ctypes.c_float), ("half_range", ctypes.c_float),
+        ("bg_color", ctypes.c_float), ("normal_pow", ctypes.c_float),
+        ("blob", _fp), ("cb", _fp), ("beta_param", _fp),
+        ("cam_loc", _fp), ("ray_dirs", _fp), ("depth_fac", _fp), ("scale_dist", _fp), ("t_vals", _fp), ("jitter", _fp),
+        ("points", _fp),
+        ("rgb", _fp), ("mask", _fp), ("mask_hard", _fp), ("depth", _fp), ("normal", _fp),
+        ("sdf", _fp), ("feat", _fp), ("grad", _fp),
+        ("rgb_bar", _fp), ("mask_bar", _fp), ("depth_bar", _fp), ("normal_bar", _fp), ("sdf_bar", _fp), ("grad_bar", _fp),
+        ("grad_partial", _fp), ("cb_bar", _fp), ("ray_dirs_bar", _fp), ("depth_fac_bar", _fp), ("cam_loc_bar", _fp),
+        ("scale_dist_bar", _fp), ("points_bar", _fp),
+        ("scratch", _fp),
+    ]
+
+
+def declare(L):
+    vp, i, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    L.sc_render_blob_floats.restype = sz
+    L.sc_render_grad_floats.restype = sz
+    L.sc_render_num_ctas.restype = i
+    L.sc_render_scratch_bytes.argtypes = [i]
+    L.sc_render_scratch_bytes.restype = sz
+    L.sc_render_pack_weights.argtypes = [vp, vp, vp, vp]
+    L.sc_render_pack_weights.restype = i
+    L.sc_render_latent_bias.argtypes = [vp, vp, vp, i, vp, vp]
+    L.sc_render_latent_bias.restype = i
+    L.sc_render_forward.argtypes = [ctypes.POINTER(ScRenderArgs), vp]
+    L.sc_render_forward.restype = i
+    if hasattr(L, "sc_render_backward"):
+        L.sc_render_backward.argtypes = [ctypes.POINTER(ScRenderArgs), vp]
+        L.sc_render_backward.restype = i
+        L.sc_render_grad_finalize.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp]
+        L.sc_render_grad_finalize.restype = i
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise TypeError("shapeclipper_b200 kernels take float32 tensors (got %s)" % t.dtype)
+    return t.contiguous()
+
+
+def pack_weights(weights, biases):
+    """weights/biases: 10 CUDA fp32 tensors each (sdf lin0..5, rgb lin0..3, nn.Linear layout) -> blob tensor."""
+    L = _lib.lib()
+    dev = weights[0].device
+    _lib.require_cuda(*weights, *biases)
+    ws = [_f32c(w.detach()) for w in weights]
+    bs = [_f32c(b.detach()) for b in biases]
+    blob = torch.empty(L.sc_render_blob_floats(), dtype=torch.float32, device=dev)
+    warr = (ctypes.c_void_p * 10)(*[w.data_ptr() for w in ws])
+    barr = (ctypes.c_void_p * 10)(*[b.data_ptr() for b in bs])
+    with torch.cuda.device(dev):
+        _lib.check(L.sc_render_pack_weights(warr, barr, _p(blob), _lib.stream_of(blob)), "sc_render_pack_weights")
+    return blob
+
+
+def latent_bias(blob, z_sdf, z_rgb, batch):
+    L = _lib.lib()
+    cb = torch.empty(batch, 4, 64, dtype=torch.float32, device=blob.device)
+    zs = _f32c(z_sdf.detach()) if z_sdf is not None else None
+    zr = _f32c(z_rgb.detach()) if z_rgb is not None else None
+    with torch.cuda.device(blob.device):
+        _lib.check(L.sc_render_latent_bias(_p(blob), _p(zs), _p(zr), batch, _p(cb), _lib.stream_of(blob)),
+                   "sc_render_latent_bias")
+    return cb
+
+
+def scratch(device, backward):
+    L = _lib.lib()
+    with torch.cuda.device(device):
+        n = L.sc_render_scratch_bytes(1 if backward else 0)
+    return torch.empty(n // 4, dtype=torch.float32, device=device)
+
+
+def launch_forward(args, device):
+    L = _lib.lib()
+    with torch.cuda.device(device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(L.sc_render_forward(ctypes.byref(args), stream), "sc_render_forward")
+
+
+def launch_backward(args, device):
+    L = _lib.lib()
+    with torch.cuda.device(device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(L.sc_render_backward(ctypes.byref(args), stream), "sc_render_backward")

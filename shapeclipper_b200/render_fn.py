@@ -1,0 +1,208 @@
+"""torch.autograd glue between the reference-shaped modules (renderer.py / implicit.py) and the C ABI
+(sc_render_forward / sc_render_backward / sc_render_grad_finalize). All arithmetic happens in the CUDA library."""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import _render_native as rn
+
+_N_SDF, _N_RGB = 6, 4
+
+
+def _params_of(sdf_net, rgb_net, device):
+    ws = [l.weight for l in sdf_net.linears()]
+    bs = [l.bias for l in sdf_net.linears()]
+    if rgb_net is not None:
+        ws += [l.weight for l in rgb_net.linears()]
+        bs += [l.bias for l in rgb_net.linears()]
+    return ws, bs
+
+
+_dummy_rgb = {}
+
+
+def _dummy_rgb_params(device):
+    key = str(device)
+    if key not in _dummy_rgb:
+        shapes = [(64, 167), (64, 64), (64, 64), (3, 64)]
+        _dummy_rgb[key] = ([torch.zeros(s, device=device) for s in shapes],
+                           [torch.zeros(s[0], device=device) for s in shapes])
+    return _dummy_rgb[key]
+
+
+def _new_args(**kw):
+    a = rn.ScRenderArgs()
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            v = ctypes.c_void_p(v.data_ptr())
+        setattr(a, k, v)
+    return a
+
+
+def _finalize(L, partial, n_ctas, cb_bar, z_sdf, z_rgb, blob, B, ws, bs, need_rgb):
+    """-> (grads for weights[10], biases[10] (None where not produced), z_sdf_bar, z_rgb_bar, beta_eff_bar)."""
+    dev = blob.device
+    gw = [torch.empty_like(w) for w in ws[:_N_SDF]] + ([torch.empty_like(w) for w in ws[_N_SDF:]] if need_rgb else [None] * _N_RGB)
+    gb = [torch.empty_like(b) for b in bs[:_N_SDF]] + ([torch.empty_like(b) for b in bs[_N_SDF:]] if need_rgb else [None] * _N_RGB)
+    warr = (ctypes.c_void_p * 10)(*[(g.data_ptr() if g is not None else None) for g in gw])
+    barr = (ctypes.c_void_p * 10)(*[(g.data_ptr() if g is not None else None) for g in gb])
+    z_sdf_bar = torch.empty(B, 64, device=dev)
+    z_rgb_bar = torch.empty(B, 64, device=dev) if need_rgb else None
+    beta_bar = torch.empty(1, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.sc_render_grad_finalize(rn._p(partial), n_ctas, rn._p(cb_bar), rn._p(z_sdf), rn._p(z_rgb), rn._p(blob), B,
+                                             warr, barr, rn._p(z_sdf_bar), rn._p(z_rgb_bar), rn._p(beta_bar),
+                                             ), "sc_render_grad_finalize")
+    return gw, gb, z_sdf_bar, z_rgb_bar, beta_bar
+
+
+class _RenderFn(torch.autograd.Function):
+    """Renderer.forward minus ray generation and the eikonal branch (model/renderer.py:80-152)."""
+
+    @staticmethod
+    def forward(ctx, cfg, beta_param, cam_loc, ray_dirs, depth_fac, scale_dist, z_sdf, z_rgb, t_vals, jitter, *params):
+        L = _lib.lib()
+        _lib.require_cuda(cam_loc, ray_dirs, depth_fac, scale_dist, z_sdf, z_rgb, beta_param, *params)
+        dev = ray_dirs.device
+        B, R = ray_dirs.shape[0], ray_dirs.shape[1]
+        ws, bs = list(params[:10]), list(params[10:])
+        blob = rn.pack_weights(ws, bs)
+        cb = rn.latent_bias(blob, z_sdf, z_rgb, B)
+        f = lambda t: rn._f32c(t.detach())
+        cam_loc, ray_dirs, depth_fac, scale_dist = f(cam_loc), f(ray_dirs), f(depth_fac), f(scale_dist)
+        jit = f(jitter) if jitter is not None else None
+        t_vals = f(t_vals)
+        rgb = torch.empty(B, R, 3, device=dev); normal = torch.empty(B, R, 3, device=dev)
+        mask = torch.empty(B, R, 1, device=dev); mask_hard = torch.empty(B, R, 1, device=dev)
+        depth = torch.empty(B, R, 1, device=dev)
+        scratch = rn.scratch(dev, backward=False)
+        beta_c = f(beta_param).reshape(1)
+        args = _new_args(mode=0, batch=B, n_per_image=R, n_samples=cfg["n_samples"], beta_min=cfg["beta_min"],
+                         cam_dist=cfg["cam_dist"], half_range=cfg["half_range"], bg_color=cfg["bg_color"],
+                         normal_pow=cfg["normal_pow"], blob=blob, cb=cb, beta_param=beta_c, cam_loc=cam_loc,
+                         ray_dirs=ray_dirs, depth_fac=depth_fac, scale_dist=scale_dist, t_vals=t_vals,
+                         rgb=rgb, mask=mask, mask_hard=mask_hard, depth=depth, normal=normal, scratch=scratch)
+        if jit is not None:
+            args.jitter = ctypes.c_void_p(jit.data_ptr())
+        rn.launch_forward(args, dev)
+        ctx.cfg = cfg
+        ctx.has_jitter = jit is not None
+        ctx.save_for_backward(blob, cb, beta_c, cam_loc, ray_dirs, depth_fac, scale_dist, t_vals,
+                              jit if jit is not None else t_vals, f(z_sdf), f(z_rgb), *params)
+        ctx.mark_non_differentiable(mask_hard)
+        ctx.set_materialize_grads(False)
+        return rgb, mask, mask_hard, depth, normal
+
+    @staticmethod
+    def backward(ctx, rgb_bar, mask_bar, _mh_bar, depth_bar, normal_bar):
+        L = _lib.lib()
+        saved = ctx.saved_tensors
+        blob, cb, beta_c, cam_loc, ray_dirs, depth_fac, scale_dist, t_vals, jit, z_sdf, z_rgb = saved[:11]
+        params = saved[11:]
+        ws, bs = list(params[:10]), list(params[10:])
+        cfg = ctx.cfg
+        dev = ray_dirs.device
+        B, R = ray_dirs.shape[0], ray_dirs.shape[1]
+        g = lambda t: rn._f32c(t) if t is not None else None
+        rgb_bar, mask_bar, depth_bar, normal_bar = g(rgb_bar), g(mask_bar), g(depth_bar), g(normal_bar)
+        n_ctas = L.sc_render_num_ctas()
+        partial = torch.empty(n_ctas, L.sc_render_grad_floats(), device=dev)
+        cb_bar = torch.zeros(B, 7, 64, device=dev)
+        dirs_bar = torch.zeros(B, R, 3, device=dev); fac_bar = torch.zeros(B, R, device=dev)
+        loc_bar = torch.zeros(B, 3, device=dev); sd_bar = torch.zeros(B, device=dev)
+        scratch = rn.scratch(dev, backward=True)
+        args = _new_args(mode=0, batch=B, n_per_image=R, n_samples=cfg["n_samples"], beta_min=cfg["beta_min"],
+                         cam_dist=cfg["cam_dist"], half_range=cfg["half_range"], bg_color=cfg["bg_color"],
+                         normal_pow=cfg["normal_pow"], blob=blob, cb=cb, beta_param=beta_c, cam_loc=cam_loc,
+                         ray_dirs=ray_dirs, depth_fac=depth_fac, scale_dist=scale_dist, t_vals=t_vals,
+                         grad_partial=partial, cb_bar=cb_bar, ray_dirs_bar=dirs_bar, depth_fac_bar=fac_bar,
+                         cam_loc_bar=loc_bar, scale_dist_bar=sd_bar, scratch=scratch)
+        if ctx.has_jitter:
+            args.jitter = ctypes.c_void_p(jit.data_ptr())
+        for name, t in (("rgb_bar", rgb_bar), ("mask_bar", mask_bar), ("depth_bar", depth_bar), ("normal_bar", normal_bar)):
+            if t is not None:
+                setattr(args, name, ctypes.c_void_p(t.data_ptr()))
+        rn.launch_backward(args, dev)
+        gw, gb, z_sdf_bar, z_rgb_bar, beta_bar = _finalize(L, partial, n_ctas, cb_bar, z_sdf, z_rgb, blob, B, ws, bs, True)
+        beta_param_bar = (beta_bar * torch.sign(beta_c)).reshape(())
+        return (None, beta_param_bar, loc_bar, dirs_bar, fac_bar, sd_bar, z_sdf_bar, z_rgb_bar, None, None, *gw, *gb)
+
+
+class _SDFQueryFn(torch.autograd.Function):
+    """SDFNetwork.get_conditional_output (model/implicit.py:163-189): sdf, features and d sdf / d x."""
+
+    @staticmethod
+    def forward(ctx, B, want_grad, detach_latent, points, z_sdf, *params):
+        L = _lib.lib()
+        _lib.require_cuda(points, z_sdf, *params)
+        dev = points.device
+        P = points.shape[0]
+        if P % B != 0:
+            raise ValueError("points_flat must hold batch_size * N points (batch-major)")
+        N = P // B
+        dw, db = _dummy_rgb_params(dev)
+        ws = list(params[:6]) + dw
+        bs = list(params[6:]) + db
+        blob = rn.pack_weights(ws, bs)
+        cb = rn.latent_bias(blob, z_sdf, None, B)
+        pts = rn._f32c(points.detach())
+        sdf = torch.empty(P, 1, device=dev); feat = torch.empty(P, 64, device=dev)
+        grad = torch.empty(P, 3, device=dev) if want_grad else None
+        scratch = rn.scratch(dev, backward=False)
+        args = _new_args(mode=1, batch=B, n_per_image=N, n_samples=1, want_grad=int(want_grad), want_feat=1,
+                         beta_min=1e-4, blob=blob, cb=cb, points=pts, sdf=sdf, feat=feat, scratch=scratch)
+        if grad is not None:
+            args.grad = ctypes.c_void_p(grad.data_ptr())
+        rn.launch_forward(args, dev)
+        ctx.meta = (B, N, want_grad, detach_latent)
+        ctx.save_for_backward(blob, cb, pts, rn._f32c(z_sdf.detach()), *params)
+        ctx.set_materialize_grads(False)
+        if grad is None:
+            grad = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(grad)
+        return sdf, feat, grad
+
+    @staticmethod
+    def backward(ctx, sdf_bar, feat_bar, grad_bar):
+        if feat_bar is not None:
+            raise NotImplementedError("gradients through the SDF feature output of get_conditional_output are only "
+                                      "supported inside Renderer.forward (the reference never needs them elsewhere)")
+        L = _lib.lib()
+        blob, cb, pts, z_sdf = ctx.saved_tensors[:4]
+        params = ctx.saved_tensors[4:]
+        B, N, want_grad, detach_latent = ctx.meta
+        dev = pts.device
+        dw, db = _dummy_rgb_params(dev)
+        ws, bs = list(params[:6]) + dw, list(params[6:]) + db
+        n_ctas = L.sc_render_num_ctas()
+        partial = torch.empty(n_ctas, L.sc_render_grad_floats(), device=dev)
+        cb_bar = torch.zeros(B, 7, 64, device=dev)
+        pts_bar = torch.zeros(B * N, 3, device=dev)
+        scratch = rn.scratch(dev, backward=True)
+        args = _new_args(mode=1, batch=B, n_per_image=N, n_samples=1, want_grad=int(want_grad and grad_bar is not None),
+                         want_feat=0, detach_latent=int(detach_latent), beta_min=1e-4, blob=blob, cb=cb, points=pts,
+                         grad_partial=partial, cb_bar=cb_bar, points_bar=pts_bar, scratch=scratch)
+        if sdf_bar is not None:
+            keep1 = rn._f32c(sdf_bar)
+            args.sdf_bar = ctypes.c_void_p(keep1.data_ptr())
+        if grad_bar is not None and want_grad:
+            keep2 = rn._f32c(grad_bar)
+            args.grad_bar = ctypes.c_void_p(keep2.data_ptr())
+        rn.launch_backward(args, dev)
+        gw, gb, z_sdf_bar, _, _ = _finalize(L, partial, n_ctas, cb_bar, z_sdf, None, blob, B, ws, bs, False)
+        return (None, None, None, pts_bar, (None if detach_latent else z_sdf_bar), *gw[:6], *gb[:6])
+
+
+def sdf_query(sdf_net, opt, batch_size, points_flat, proj_latent, want_grad, detach_latent):
+    ws = [l.weight for l in sdf_net.linears()]
+    bs = [l.bias for l in sdf_net.linears()]
+    sdf, feat, grad = _SDFQueryFn.apply(int(batch_size), bool(want_grad), bool(detach_latent), points_flat, proj_latent,
+                                        *ws, *bs)
+    return sdf, feat, (grad if want_grad else None)
+
+
+def render_rays(cfg, beta_param, cam_loc, ray_dirs, depth_fac, scale_dist, z_sdf, z_rgb, t_vals, jitter, sdf_net, rgb_net):
+    ws = [l.weight for l in sdf_net.linears()] + [l.weight for l in rgb_net.linears()]
+    bs = [l.bias for l in sdf_net.linears()] + [l.bias for l in rgb_net.linears()]
+    return _RenderFn.apply(cfg, beta_param, cam_loc, ray_dirs, depth_fac, scale_dist, z_sdf, z_rgb, t_vals, jitter, *ws, *bs)

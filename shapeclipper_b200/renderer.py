@@ -1,0 +1,94 @@
+"""Renderer with the reference's constructor/forward signature (model/renderer.py:40-185), evaluated by the fused
+sm_100a render kernels. Drop-in for `model.renderer` (see shapeclipper_b200.shim).
+
+What runs where:
+  * ray geometry from pose/intrinsics for the selected pixels: torch ops on [B,R,3] (camera.py), differentiable;
+  * stratified depths, sample points, posenc, SDF MLP + its spatial gradient, Laplace density, RGB MLP, alpha
+    compositing and the rgb/mask/depth/normal reductions, forward AND backward: one CUDA kernel each way;
+  * eikonal samples: the SDF point-query kernel (get_conditional_output) + a norm.
+The CPU-generator draws happen in the reference's order (rand -> randint -> uniform_) so equal seeds give equal
+samples.
+"""
+import torch
+import torch.nn as nn
+
+from . import camera
+from .implicit import LaplaceDensity
+from .render_fn import render_rays
+
+
+class UniformSampler(nn.Module):
+    """Depth sampler of the reference (model/renderer.py:8-37). The depths themselves are produced inside the render
+    kernel; this class keeps the attribute surface and restates z for the eikonal sample (one depth per ray)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.N_samples = opt.render.n_samples_uniform
+
+    @staticmethod
+    def depth_at(opt, scale_dist_per_ray, t_vals, idx, u_at_idx):
+        """z of sample `idx` [N] for rays with scale_dist_per_ray [N]; u_at_idx = jitter of that sample or None."""
+        c = opt.camera.dist * scale_dist_per_ray
+        near, far = c - 0.7, c + 0.7
+        S = t_vals.shape[0]
+
+        def zb(i):
+            t = t_vals[i.clamp(0, S - 1)]
+            return near * (1.0 - t) + far * t
+        z = zb(idx)
+        if u_at_idx is None:
+            return z
+        upper = torch.where(idx < S - 1, 0.5 * (zb(idx + 1) + z), z)
+        lower = torch.where(idx > 0, 0.5 * (z + zb(idx - 1)), z)
+        return lower + (upper - lower) * u_at_idx
+
+
+class Renderer(nn.Module):
+    def __init__(self, opt, sdf_network, rgb_network):
+        super().__init__()
+        self.bg_color = opt.data.bgcolor
+        self.eik_range = opt.arch.impl_sdf.eikonal_sample_range
+        self.normal_model = opt.render.normal_model
+        self.sdf_network = sdf_network
+        self.rgb_network = rgb_network
+        self.density = LaplaceDensity(params_init={'beta': opt.arch.impl_sdf.beta_init})
+        if opt.render.sampler != 'uniform':
+            raise NotImplementedError
+        if self.normal_model != 'volume':
+            raise NotImplementedError("only render.normal_model == 'volume' (the reference default) is implemented")
+        self.ray_sampler = UniformSampler(opt)
+        self.N_samples = opt.render.n_samples_uniform
+
+    def forward(self, opt, pose, intr, scale_dist, proj_latent_sdf, proj_latent_rgb, ray_idx=None, training=True,
+                visualize=False):
+        if opt.camera.model != "perspective":
+            raise NotImplementedError("only the perspective camera of the reference config is implemented")
+        if visualize:
+            raise NotImplementedError("visualize=True (200 debug rays, model/renderer.py:174-183) is not implemented")
+        dev = pose.device
+        S = self.N_samples
+        cam_loc, ray_dirs, depth_fac = camera.pixel_rays(pose, intr, opt.H, opt.W, ray_idx)
+        B, R = ray_dirs.shape[0], ray_dirs.shape[1]
+
+        # CPU-generator draws, reference order (renderer.py:29,33,158)
+        u = torch.rand(B * R, S).to(dev) if training else None
+        eik_idx = torch.randint(S, (B * R,)).to(dev)
+        t_vals = torch.linspace(0., 1., steps=S).to(dev)
+
+        cfg = dict(n_samples=S, beta_min=float(self.density.beta_min), cam_dist=float(opt.camera.dist), half_range=0.7,
+                   bg_color=float(self.bg_color), normal_pow=float(opt.reg.normal_pow))
+        rgb, mask, mask_hard, depth, normal = render_rays(
+            cfg, self.density.beta, cam_loc, ray_dirs, depth_fac, scale_dist, proj_latent_sdf, proj_latent_rgb,
+            t_vals, u, self.sdf_network, self.rgb_network)
+
+        grad_eikonal = None
+        if training:
+            uni = torch.empty(B * R, 3).uniform_(self.eik_range[0], self.eik_range[1]).to(dev).reshape(B, R, 3)
+            sd_ray = scale_dist.unsqueeze(-1).expand(B, R).reshape(-1)
+            u_at = u.gather(1, eik_idx.unsqueeze(-1)).squeeze(-1)
+            z_eik = UniformSampler.depth_at(opt, sd_ray, t_vals, eik_idx, u_at).reshape(B, R, 1)
+            near_pts = cam_loc.unsqueeze(1) + z_eik * ray_dirs
+            eik_pts = torch.cat([uni, near_pts], dim=1).reshape(-1, 3)
+            _, _, g = self.sdf_network.get_conditional_output(opt, B, eik_pts, proj_latent_sdf, compute_grad=True)
+            grad_eikonal = g.norm(2, dim=1)
+        return rgb, mask, mask_hard, depth, normal, grad_eikonal

@@ -1,0 +1,124 @@
+"""GPU parity of the fused render / SDF-query kernels (through the C ABI and the reference-shaped modules) against
+the golden fixtures produced by the UNMODIFIED reference (tests/gen_golden.py) and against the oracle.
+Tolerance: 1e-4 relative (BASELINE.json north_star) on rgb / mask / depth / normal / sdf, stated per assert."""
+import os
+
+import pytest
+import torch
+
+from oracle import render_ref as R
+
+pytestmark = pytest.mark.gpu
+REL = 1e-4
+# Unit normals of grazing rays are ill-conditioned: on the golden fixtures the reference's own fp32 result is 1.8e-4
+# (mask 2e-3) to 1.8e-3 (mask 1e-4) away from an fp64 evaluation of the same inputs (measured with
+# oracle/render_ref.py). So normals are held to 1e-4 where it is meaningful (mask-weighted, every ray) and to 1e-3 raw
+# on rays with mask > 0.05; depth and eikonal norms (fp32-vs-fp64 1.5e-5 / 5.6e-5) to 1e-4 relative.
+REL_NORMAL_RAW = 1e-3
+
+
+def _close(got, want, name, rel=REL):
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    scale = max(float(want.abs().max()), 1e-3)
+    err = float((got - want).abs().max())
+    assert err <= rel * scale, "%s: max abs err %.3e > %.1e * %.3e" % (name, err, rel, scale)
+
+
+def _check_outputs(out, want, names):
+    got = dict(zip(names, out))
+    for nm in names:
+        if want.get(nm) is None:
+            assert got[nm] is None
+        elif nm == "mask_hard":
+            assert (got[nm].cpu() != want[nm]).float().mean() <= 1e-3
+        elif nm == "normal":
+            solid = (want["mask"] > 0.05).float()
+            _close(got[nm] * solid.to(got[nm].device), want[nm] * solid, "normal(raw, mask>0.05)", REL_NORMAL_RAW)
+            _close(got[nm] * got["mask"], want[nm] * want["mask"], "normal*mask")
+        else:
+            _close(got[nm], want[nm], nm)
+
+
+NAMES = ["rgb", "mask", "mask_hard", "depth", "normal", "grad_eik"]
+
+
+def _build(fx, H, W):
+    from shapeclipper_b200 import options
+    from shapeclipper_b200.implicit import SDFNetwork, RGBNetwork
+    from shapeclipper_b200.renderer import Renderer
+    opt = options.default_options(H=H, W=W)
+    opt.render.n_samples_uniform = fx.get("S", 64)
+    sdf, rgb = SDFNetwork(opt), RGBNetwork(opt)
+    sdf.load_state_dict(fx["sdf_params"]); rgb.load_state_dict(fx.get("rgb_params", rgb.state_dict()))
+    ren = Renderer(opt, sdf, rgb).cuda()
+    if "beta" in fx:
+        with torch.no_grad():
+            ren.density.beta.copy_(fx["beta"])
+    return opt, sdf, rgb, ren
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+
+
+def test_eval_render_matches_reference_golden(golden_dir):
+    fx = _load(golden_dir, "render_eval_12x12")
+    opt, sdf, rgb, ren = _build(fx, fx["H"], fx["W"])
+    i = {k: v.cuda() for k, v in fx["inputs"].items()}
+    with torch.no_grad():
+        out = ren(opt, i["pose"], i["intr"], i["scale_dist"], i["z_sdf"], i["z_rgb"], ray_idx=None, training=False)
+    _check_outputs(out, fx["outputs"], NAMES)
+
+
+@pytest.mark.parametrize("name", ["render_train_40rays", "render_train_full_8x8"])
+def test_training_render_forward_matches_reference_golden(golden_dir, name):
+    fx = _load(golden_dir, name)
+    opt, sdf, rgb, ren = _build(fx, fx["H"], fx["W"])
+    i = {k: v.cuda() for k, v in fx["inputs"].items()}
+    ridx = fx["ray_idx"].cuda() if fx["ray_idx"] is not None else None
+    seed = {"render_train_40rays": 2, "render_train_full_8x8": 3}[name] + 100
+    torch.manual_seed(seed)           # the generator state the reference had when it rendered (gen_golden.py)
+    out = ren(opt, i["pose"], i["intr"], i["scale_dist"], i["z_sdf"], i["z_rgb"], ray_idx=ridx, training=True)
+    _check_outputs(out, fx["outputs"], NAMES)
+
+
+def test_sdf_query_matches_reference_golden(golden_dir):
+    fx = _load(golden_dir, "sdf_query")
+    opt, sdf, _, _ = _build(fx, 16, 16)
+    s, f, g = sdf.get_conditional_output(opt, fx["B"], fx["pts"].cuda(), fx["z_sdf"].cuda(), compute_grad=True)
+    _close(s, fx["sdf"], "sdf"); _close(f, fx["feat"], "feat"); _close(g, fx["grad"], "grad")
+    s2, f2, g2 = sdf.get_conditional_output(opt, fx["B"], fx["pts"].cuda(), fx["z_sdf"].cuda(), compute_grad=False)
+    assert g2 is None
+    _close(s2, fx["sdf"], "sdf(no grad)")
+
+
+def test_render_vs_oracle_default_size():
+    """B=3, 512 random rays of a 224x224 image, S=64, fresh seed: CUDA vs the oracle restatement (fp32 CPU)."""
+    from shapeclipper_b200 import options
+    from shapeclipper_b200.implicit import SDFNetwork, RGBNetwork
+    from shapeclipper_b200.renderer import Renderer
+    torch.manual_seed(11)
+    opt = options.default_options()
+    sdf, rgb = SDFNetwork(opt), RGBNetwork(opt)
+    with torch.no_grad():
+        for p in sdf.parameters():
+            p.add_(0.02 * torch.randn_like(p))
+    ren = Renderer(opt, sdf, rgb)
+    B, Rn = 3, 512
+    az = torch.rand(B) * 6.28
+    Rm = torch.stack([torch.stack([-az.cos(), -az.sin(), torch.zeros(B)], -1),
+                      torch.stack([torch.zeros(B), torch.zeros(B), -torch.ones(B)], -1),
+                      torch.stack([az.sin(), -az.cos(), torch.zeros(B)], -1)], 1)
+    sd = 1 + 0.1 * (torch.rand(B) - 0.5)
+    pose = torch.cat([Rm, torch.stack([torch.zeros(B), torch.zeros(B), 5 * sd], -1)[..., None]], -1)
+    intr = torch.tensor([[4. * 224, 0, 112], [0, 4. * 224, 112], [0, 0, 1]]).repeat(B, 1, 1)
+    zs, zr = torch.randn(B, 64) * 0.3, torch.randn(B, 64) * 0.3
+    ridx = torch.stack([torch.randperm(224 * 224)[:Rn] for _ in range(B)])
+    sp = {k: v.detach() for k, v in sdf.state_dict().items() if k.startswith("lin")}
+    rp = {k: v.detach() for k, v in rgb.state_dict().items()}
+    torch.manual_seed(5)
+    want = R.render(sp, rp, ren.density.beta.detach(), pose, intr, sd, zs, zr, 224, 224, ray_idx=ridx, training=True)
+    ren = ren.cuda()
+    torch.manual_seed(5)
+    got = ren(opt, pose.cuda(), intr.cuda(), sd.cuda(), zs.cuda(), zr.cuda(), ray_idx=ridx.cuda(), training=True)
+    _check_outputs(got, {k: want[k] for k in NAMES}, NAMES)
