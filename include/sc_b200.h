@@ -109,6 +109,15 @@ int sc_render_pack_weights(const float* const* w, const float* const* b, float* 
 int sc_render_latent_bias(const float* blob, const float* z_sdf, const float* z_rgb, int batch, float* cb,
                           cudaStream_t stream);
 int sc_render_forward(const ScRenderArgs* args, cudaStream_t stream);
+/* backward: same args + the *_bar adjoints; recomputes the forward per tile (no saved activations). Writes
+ * grad_partial / cb_bar / geometry adjoints; sc_render_grad_finalize turns those into nn.Linear-layout gradients:
+ * out_w/out_b = arrays of 10 device pointers (NULL entries are skipped), z_sdf_bar/z_rgb_bar [B,64],
+ * beta_bar = d/d(|beta|+beta_min) (1 float). */
+int sc_render_backward(const ScRenderArgs* args, cudaStream_t stream);
+int sc_render_grad_finalize(const float* grad_partial, int n_ctas, const float* cb_bar, const float* z_sdf,
+                            const float* z_rgb, const float* blob, int batch, float* const* out_w,
+                            float* const* out_b, float* z_sdf_bar, float* z_rgb_bar, float* beta_bar,
+                            cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -43,7 +43,7 @@ def declare(L):
     if hasattr(L, "sc_render_backward"):
         L.sc_render_backward.argtypes = [ctypes.POINTER(ScRenderArgs), vp]
         L.sc_render_backward.restype = i
-        L.sc_render_grad_finalize.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp]
+        L.sc_render_grad_finalize.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp]
         L.sc_render_grad_finalize.restype = i
 
 

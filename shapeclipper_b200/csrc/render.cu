@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_fwd_kernel(const ScRenderA
     T.stash = stash_base + (size_t)blockIdx.x * stash_rows * LD;
     T.S = (MODE == 0) ? a.n_samples : 1;
     T.rays_per_tile = (MODE == 0) ? M_TILE / a.n_samples : M_TILE;
-    T.beta = fabsf(*a.beta_param) + a.beta_min;
+    T.beta = (MODE == 0) ? fabsf(*a.beta_param) + a.beta_min : 1.f;
 
     const bool want_grad = (MODE == 0) || a.want_grad;
     const bool want_feat = (MODE == 0) || a.want_feat;

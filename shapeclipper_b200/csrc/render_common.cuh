@@ -117,11 +117,11 @@ constexpr int SM_PT = SM_CB + 256;                 // per-point vectors, kPtVecs
 enum PtVec : int {
     PV_Z = 0, PV_SGN, PV_SDF, PV_SIG, PV_CF, PV_UN, PV_GX0, PV_GX1, PV_GX2, PV_NS0, PV_NS1, PV_NS2,
     PV_COL0, PV_COL1, PV_COL2, PV_X0, PV_X1, PV_X2,
-    PV_SDFB, PV_GXB0, PV_GXB1, PV_GXB2, PV_CB0, PV_CB1, PV_CB2, PV_ZB, PV_XTB0, PV_XTB1, PV_XTB2, PV_W,
+    PV_SDFB, PV_GXB0, PV_GXB1, PV_GXB2, PV_CB0, PV_CB1, PV_CB2, PV_ZB, PV_XTB0, PV_XTB1, PV_XTB2, PV_W, PV_TMP,
     kPtVecs
 };
-constexpr int SM_RAY = SM_PT + kPtVecs * M_TILE;   // per-ray scratch (<= 32 rays x 16 floats)
-constexpr int SM_FLOATS = SM_RAY + 32 * 16;
+constexpr int SM_RAY = SM_PT + kPtVecs * M_TILE;   // per-ray scratch (<= 32 rays x 32 floats)
+constexpr int SM_FLOATS = SM_RAY + 32 * 32;
 constexpr int SM_BAR_BYTES = 32;                   // 2 mbarriers (+pad), placed after the float area
 constexpr size_t kSmemBytes = (size_t)SM_FLOATS * 4 + SM_BAR_BYTES;
 

@@ -53,7 +53,7 @@ def _finalize(L, partial, n_ctas, cb_bar, z_sdf, z_rgb, blob, B, ws, bs, need_rg
     with torch.cuda.device(dev):
         _lib.check(L.sc_render_grad_finalize(rn._p(partial), n_ctas, rn._p(cb_bar), rn._p(z_sdf), rn._p(z_rgb), rn._p(blob), B,
                                              warr, barr, rn._p(z_sdf_bar), rn._p(z_rgb_bar), rn._p(beta_bar),
-                                             ), "sc_render_grad_finalize")
+                                             _lib.stream_of(blob)), "sc_render_grad_finalize")
     return gw, gb, z_sdf_bar, z_rgb_bar, beta_bar
 
 

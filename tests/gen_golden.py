@@ -84,6 +84,23 @@ def case_render(mods, name, H, W, B, n_rays, training, seed):
         keys = list(params.keys()) + list(leaves.keys())
         fx["cotangents"] = cot
         fx["grads"] = {k: (g.detach().clone() if g is not None else None) for k, g in zip(keys, grads)}
+    # fp64 evaluation of the same inputs/draws with the oracle restatement ("truth"): lets the GPU tests bound their
+    # error by the reference's own fp32 rounding noise on ill-conditioned entries (grazing-ray normals, beta).
+    dt = torch.float64
+    c64 = lambda t: t.detach().to(dt) if t.is_floating_point() else t.detach()
+    sp64 = {k: c64(v).requires_grad_(training) for k, v in sdf.state_dict().items()}
+    rp64 = {k: c64(v).requires_grad_(training) for k, v in rgb.state_dict().items()}
+    in64 = {k: c64(v).requires_grad_(training) for k, v in leaves.items()}
+    beta64 = c64(ren.density.beta).requires_grad_(training)
+    o64 = R.render(sp64, rp64, beta64, in64["pose"], in64["intr"], in64["scale_dist"], in64["z_sdf"], in64["z_rgb"],
+                   H, W, ray_idx=ray_idx, training=training, rng=(u, eik_idx, eik_pts))
+    fx["outputs64"] = {n: (o64[n].detach().clone() if o64[n] is not None else None) for n in names}
+    if training:
+        scalar64 = sum((cot[n].to(dt) * o64[n].view_as(cot[n])).sum() for n in cot)
+        wrt64 = [beta64] + list(sp64.values()) + list(rp64.values()) + list(in64.values())
+        keys64 = ["density.beta"] + ["sdf_network." + k for k in sp64] + ["rgb_network." + k for k in rp64] + list(in64.keys())
+        g64 = torch.autograd.grad(scalar64, wrt64, allow_unused=True)
+        fx["grads64"] = {k: (g.detach().clone() if g is not None else None) for k, g in zip(keys64, g64)}
     torch.save(fx, os.path.join(OUT, name + ".pt"))
     print("wrote", name, {n: (tuple(o.shape) if o is not None else None) for n, o in fx["outputs"].items()})
 

@@ -24,19 +24,30 @@ def _close(got, want, name, rel=REL):
     assert err <= rel * scale, "%s: max abs err %.3e > %.1e * %.3e" % (name, err, rel, scale)
 
 
-def _check_outputs(out, want, names):
+def _check_outputs(out, want, names, truth=None):
+    """rgb / mask: 1e-4 relative against the reference's fp32 output (north_star). Every output additionally against
+    the fp64 evaluation (`truth`) when the fixture has one: error <= max(1e-4 * scale, 4 x the reference's own fp32
+    error on that tensor) — unit normals of grazing rays and eikonal norms are ill-conditioned in fp32."""
     got = dict(zip(names, out))
     for nm in names:
         if want.get(nm) is None:
             assert got[nm] is None
-        elif nm == "mask_hard":
+            continue
+        if nm == "mask_hard":
             assert (got[nm].cpu() != want[nm]).float().mean() <= 1e-3
-        elif nm == "normal":
-            solid = (want["mask"] > 0.05).float()
-            _close(got[nm] * solid.to(got[nm].device), want[nm] * solid, "normal(raw, mask>0.05)", REL_NORMAL_RAW)
-            _close(got[nm] * got["mask"], want[nm] * want["mask"], "normal*mask")
-        else:
+            continue
+        if nm in ("rgb", "mask", "depth"):
             _close(got[nm], want[nm], nm)
+        if nm == "normal":
+            _close(got[nm] * got["mask"], want[nm] * want["mask"], "normal*mask")
+        if truth is not None and truth.get(nm) is not None:
+            t = truth[nm].double().reshape(want[nm].shape)
+            scale = max(float(t.abs().max()), 1e-3)
+            e_ref = float((want[nm].double() - t).abs().max())
+            e_got = float((got[nm].detach().cpu().double() - t).abs().max())
+            assert e_got <= max(REL * scale, 4 * e_ref), "%s: err vs fp64 %.3e, reference fp32 err %.3e" % (nm, e_got, e_ref)
+        elif nm in ("normal", "grad_eik"):
+            _close(got[nm], want[nm], nm, REL_NORMAL_RAW)
 
 
 NAMES = ["rgb", "mask", "mask_hard", "depth", "normal", "grad_eik"]
@@ -67,7 +78,7 @@ def test_eval_render_matches_reference_golden(golden_dir):
     i = {k: v.cuda() for k, v in fx["inputs"].items()}
     with torch.no_grad():
         out = ren(opt, i["pose"], i["intr"], i["scale_dist"], i["z_sdf"], i["z_rgb"], ray_idx=None, training=False)
-    _check_outputs(out, fx["outputs"], NAMES)
+    _check_outputs(out, fx["outputs"], NAMES, fx.get("outputs64"))
 
 
 @pytest.mark.parametrize("name", ["render_train_40rays", "render_train_full_8x8"])
@@ -79,7 +90,7 @@ def test_training_render_forward_matches_reference_golden(golden_dir, name):
     seed = {"render_train_40rays": 2, "render_train_full_8x8": 3}[name] + 100
     torch.manual_seed(seed)           # the generator state the reference had when it rendered (gen_golden.py)
     out = ren(opt, i["pose"], i["intr"], i["scale_dist"], i["z_sdf"], i["z_rgb"], ray_idx=ridx, training=True)
-    _check_outputs(out, fx["outputs"], NAMES)
+    _check_outputs(out, fx["outputs"], NAMES, fx.get("outputs64"))
 
 
 def test_sdf_query_matches_reference_golden(golden_dir):
@@ -122,3 +133,74 @@ def test_render_vs_oracle_default_size():
     torch.manual_seed(5)
     got = ren(opt, pose.cuda(), intr.cuda(), sd.cuda(), zs.cuda(), zr.cuda(), ray_idx=ridx.cuda(), training=True)
     _check_outputs(got, {k: want[k] for k in NAMES}, NAMES)
+
+
+# ---------------------------------------------------------------------------------------------------- backward
+def _grad_close(got, want, name, rel):
+    got, want = got.detach().float().cpu(), want.detach().float().cpu()
+    scale = max(float(want.abs().max()), 1e-6)
+    err = float((got - want).abs().max())
+    assert err <= rel * scale, "grad %s: max abs err %.3e > %.1e * max|ref| %.3e" % (name, err, rel, scale)
+
+
+@pytest.mark.parametrize("name", ["render_train_40rays", "render_train_full_8x8"])
+def test_training_backward_matches_reference_autograd(golden_dir, name):
+    """Every gradient the reference's autograd produces for one scalar (fixed cotangents on rgb / mask / depth /
+    normal / eikonal norms): MLP weights and biases, beta, both latents, pose, intrinsics, scale_dist.
+    Judged against an fp64 evaluation of the same fixture: per tensor, max error / max|grad| must be <= 5e-4 or
+    <= 6 x the error of the reference's own fp32 autograd result (its double backward is reproducible to 1e-4..1e-3;
+    beta is dominated by one grazing ray whose normal adjoint is amplified by 1/|sum w n| ~ 500)."""
+    fx = _load(golden_dir, name)
+    opt, sdf, rgb, ren = _build(fx, fx["H"], fx["W"])
+    leaves = {k: v.cuda().requires_grad_(True) for k, v in fx["inputs"].items()}
+    ridx = fx["ray_idx"].cuda() if fx["ray_idx"] is not None else None
+    seed = {"render_train_40rays": 2, "render_train_full_8x8": 3}[name] + 100
+    torch.manual_seed(seed)
+    out = ren(opt, leaves["pose"], leaves["intr"], leaves["scale_dist"], leaves["z_sdf"], leaves["z_rgb"],
+              ray_idx=ridx, training=True)
+    got = dict(zip(NAMES, out))
+    scalar = sum((fx["cotangents"][n].cuda() * got[n]).sum() for n in fx["cotangents"])
+    params = dict(ren.named_parameters())
+    keys = list(params.keys()) + list(leaves.keys())
+    grads = torch.autograd.grad(scalar, list(params.values()) + list(leaves.values()), allow_unused=True)
+    report, bad = {}, {}
+    for k, g in zip(keys, grads):
+        want, truth = fx["grads"][k], fx["grads64"][k]
+        if want is None:
+            continue
+        assert g is not None, k
+        scale = max(float(truth.abs().max()), 1e-6)
+        e_ref = float((want.double() - truth).abs().max()) / scale
+        e_got = float((g.detach().cpu().double() - truth).abs().max()) / scale
+        report[k] = "%.1e (ref %.1e)" % (e_got, e_ref)
+        if e_got > max(5e-4, 6 * e_ref):
+            bad[k] = report[k]
+    print(report)
+    assert not bad, bad
+
+
+def test_sdf_query_backward_first_order_only():
+    """compute_grad=False path (pretrainer / level grid): d loss / d (weights, latent, points) vs oracle autograd."""
+    from shapeclipper_b200 import options
+    from shapeclipper_b200.implicit import SDFNetwork
+    torch.manual_seed(21)
+    opt = options.default_options()
+    net = SDFNetwork(opt)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(0.02 * torch.randn_like(p))
+    B, N = 2, 300
+    pts = (torch.rand(B * N, 3) - 0.5) * 1.6
+    z = torch.randn(B, 64) * 0.3
+    cot = torch.randn(B * N, 1)
+    sp = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    zr, pr = z.clone().requires_grad_(True), pts.clone().requires_grad_(True)
+    s_ref, _, _ = R.sdf_query(sp, pr, zr, B, want_grad=False)
+    ref = torch.autograd.grad((s_ref * cot).sum(), [zr, pr] + list(sp.values()))
+    net = net.cuda()
+    zc, pc = z.cuda().requires_grad_(True), pts.cuda().requires_grad_(True)
+    s, f, g = net.get_conditional_output(opt, B, pc, zc, compute_grad=False)
+    got = torch.autograd.grad((s * cot.cuda()).sum(), [zc, pc] + [dict(net.named_parameters())[k] for k in sp])
+    _close(s, s_ref, "sdf")
+    for k, a, b in zip(["z", "pts"] + list(sp.keys()), got, ref):
+        _grad_close(a, b, k, 1e-3)
