@@ -69,7 +69,31 @@ def pack_weights(weights, biases):
     barr = (ctypes.c_void_p * 10)(*[b.data_ptr() for b in bs])
     with torch.cuda.device(dev):
         _lib.check(L.sc_render_pack_weights(warr, barr, _p(blob), _lib.stream_of(blob)), "sc_render_pack_weights")
+    TIMERS.count()
     return blob
+
+
+_blob_cache = {}
+
+
+def packed_blob(weights, biases):
+    """pack_weights with a small cache keyed on (storage, version) of every tensor: the kernel calls of one
+    training step share one packing per parameter set. In-place updates through autograd-visible ops (optimisers,
+    load_state_dict) bump the version; after raw `.data` writes call invalidate_blob_cache()."""
+    key = tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases))
+    dev = str(weights[0].device)
+    cache = _blob_cache.setdefault(dev, {})
+    blob = cache.get(key)
+    if blob is None:
+        if len(cache) >= 4:
+            cache.clear()
+        blob = pack_weights(weights, biases)
+        cache[key] = blob
+    return blob
+
+
+def invalidate_blob_cache():
+    _blob_cache.clear()
 
 
 def latent_bias(blob, z_sdf, z_rgb, batch):
@@ -80,6 +104,7 @@ def latent_bias(blob, z_sdf, z_rgb, batch):
     with torch.cuda.device(blob.device):
         _lib.check(L.sc_render_latent_bias(_p(blob), _p(zs), _p(zr), batch, _p(cb), _lib.stream_of(blob)),
                    "sc_render_latent_bias")
+    TIMERS.count()
     return cb
 
 
@@ -90,15 +115,64 @@ def scratch(device, backward):
     return torch.empty(n // 4, dtype=torch.float32, device=device)
 
 
+class KernelTimers:
+    """Optional CUDA-event timing of the main kernels on their launch stream (bench.py's roofline numbers).
+    Also counts every launch of a kernel of this library (bench.py's gpu_launches)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events = {}
+        self.launches = 0
+
+    def reset(self):
+        self.events = {}
+        self.launches = 0
+
+    def count(self, n=1):
+        self.launches += n
+
+    def span(self, name, device):
+        return _Span(self, name, device)
+
+    def totals_ms(self):
+        torch.cuda.synchronize()
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.events.items()}
+
+
+class _Span:
+    def __init__(self, timers, name, device):
+        self.t, self.name, self.device = timers, name, device
+
+    def __enter__(self):
+        if self.t.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if self.t.enabled:
+            self.b.record(torch.cuda.current_stream(self.device))
+            self.t.events.setdefault(self.name, []).append((self.a, self.b))
+        return False
+
+
+TIMERS = KernelTimers()
+
+
 def launch_forward(args, device):
     L = _lib.lib()
     with torch.cuda.device(device):
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        _lib.check(L.sc_render_forward(ctypes.byref(args), stream), "sc_render_forward")
+        with TIMERS.span("render_fwd" if args.mode == 0 else "sdf_query_fwd", device):
+            _lib.check(L.sc_render_forward(ctypes.byref(args), stream), "sc_render_forward")
+    TIMERS.count()
 
 
 def launch_backward(args, device):
     L = _lib.lib()
     with torch.cuda.device(device):
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        _lib.check(L.sc_render_backward(ctypes.byref(args), stream), "sc_render_backward")
+        with TIMERS.span("render_bwd" if args.mode == 0 else "sdf_query_bwd", device):
+            _lib.check(L.sc_render_backward(ctypes.byref(args), stream), "sc_render_backward")
+    TIMERS.count()

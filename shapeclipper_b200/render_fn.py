@@ -54,6 +54,7 @@ def _finalize(L, partial, n_ctas, cb_bar, z_sdf, z_rgb, blob, B, ws, bs, need_rg
         _lib.check(L.sc_render_grad_finalize(rn._p(partial), n_ctas, rn._p(cb_bar), rn._p(z_sdf), rn._p(z_rgb), rn._p(blob), B,
                                              warr, barr, rn._p(z_sdf_bar), rn._p(z_rgb_bar), rn._p(beta_bar),
                                              _lib.stream_of(blob)), "sc_render_grad_finalize")
+    rn.TIMERS.count()
     return gw, gb, z_sdf_bar, z_rgb_bar, beta_bar
 
 
@@ -67,7 +68,7 @@ class _RenderFn(torch.autograd.Function):
         dev = ray_dirs.device
         B, R = ray_dirs.shape[0], ray_dirs.shape[1]
         ws, bs = list(params[:10]), list(params[10:])
-        blob = rn.pack_weights(ws, bs)
+        blob = rn.packed_blob(ws, bs)
         cb = rn.latent_bias(blob, z_sdf, z_rgb, B)
         f = lambda t: rn._f32c(t.detach())
         cam_loc, ray_dirs, depth_fac, scale_dist = f(cam_loc), f(ray_dirs), f(depth_fac), f(scale_dist)
@@ -144,7 +145,7 @@ class _SDFQueryFn(torch.autograd.Function):
         dw, db = _dummy_rgb_params(dev)
         ws = list(params[:6]) + dw
         bs = list(params[6:]) + db
-        blob = rn.pack_weights(ws, bs)
+        blob = rn.packed_blob(ws, bs)
         cb = rn.latent_bias(blob, z_sdf, None, B)
         pts = rn._f32c(points.detach())
         sdf = torch.empty(P, 1, device=dev); feat = torch.empty(P, 64, device=dev)
