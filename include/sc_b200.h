@@ -8,6 +8,8 @@
  * Reference interfaces replaced (paths relative to the reference tree):
  *   sc_chamfer_forward   external/chamfer3D/chamfer_cuda.cpp:17-19  chamfer_forward  -> chamfer3D.cu:137-154
  *   sc_chamfer_backward  external/chamfer3D/chamfer_cuda.cpp:22-26  chamfer_backward -> chamfer3D.cu:176-195
+ *   sc_clip_encode       CLIP_anno.py:166 clip_model.encode_image (openai/CLIP VisionTransformer)
+ *   sc_cosine_topk       CLIP_anno.py:29-57 NN_annotator.calc_matches
  *   sc_render_*          model/renderer.py:57 Renderer.forward, model/implicit.py:163 get_conditional_output
  */
 #ifndef SC_B200_H_
@@ -118,6 +120,54 @@ int sc_render_grad_finalize(const float* grad_partial, int n_ctas, const float* 
                             const float* z_rgb, const float* blob, int batch, float* const* out_w,
                             float* const* out_b, float* z_sdf_bar, float* z_rgb_bar, float* beta_bar,
                             cudaStream_t stream);
+
+/* ---- CLIP ViT image tower + cosine k-NN ------------------------------------------
+ * Replaces clip_model.encode_image + F.normalize (CLIP_anno.py:166-167; openai/CLIP, un-vendored dependency) and
+ * NN_annotator.calc_matches (CLIP_anno.py:29-57). GEMMs run on tcgen05 tensor cores from TMA-staged bf16 tiles with
+ * fp32 TMEM accumulation; with `split` set every operand is a hi/lo bf16 pair and each product is 3 MMAs
+ * (fp32-class accuracy); otherwise plain bf16 (throughput mode).
+ * Weight matrices are [out,in] row-major bf16 planes (lo planes may be NULL when split == 0); vectors are fp32. */
+typedef struct ScClipConfig {
+    int image_size;   /* 224 */
+    int patch;        /* 32 (ViT-B/32) or 14 (ViT-L/14) */
+    int width;        /* 768 / 1024 ; heads * 64 */
+    int layers;       /* 12 / 24 */
+    int heads;        /* 12 / 16 */
+    int out_dim;      /* 512 / 768 */
+    int split;        /* 1 = hi/lo operands (3 MMAs per product), 0 = plain bf16 */
+} ScClipConfig;
+typedef struct ScClipLayer {
+    const float *ln1_w, *ln1_b;
+    const void *qkv_w_hi, *qkv_w_lo; const float* qkv_b;     /* in_proj  [3W, W] */
+    const void *out_w_hi, *out_w_lo; const float* out_b;     /* out_proj [W, W]  */
+    const float *ln2_w, *ln2_b;
+    const void *fc1_w_hi, *fc1_w_lo; const float* fc1_b;     /* c_fc     [4W, W] */
+    const void *fc2_w_hi, *fc2_w_lo; const float* fc2_b;     /* c_proj   [W, 4W] */
+} ScClipLayer;
+typedef struct ScClipWeights {
+    const void *conv_w_hi, *conv_w_lo;                       /* conv1.weight viewed as [W, 3*P*P], columns zero-padded to a multiple of 64 */
+    const float *class_emb, *pos_emb;                        /* [W], [T, W] */
+    const float *lnpre_w, *lnpre_b, *lnpost_w, *lnpost_b;
+    const void *proj_w_hi, *proj_w_lo;                       /* proj^T: [out_dim, W] */
+    const ScClipLayer* layers;                               /* HOST array of cfg.layers entries (device pointers inside) */
+} ScClipWeights;
+
+/* C[M,N] = A[M,K] . W[N,K]^T * scale (+bias[N]) (act 1 = QuickGELU) (+residual fp32 [M,N]) -> out_f32 and/or hi/lo planes.
+ * a_lo / w_lo NULL => single bf16 product. K % 64 == 0, N % 64 == 0. */
+int sc_gemm_bf16_tc(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, int M, int N, int K,
+                    const float* bias, const float* residual, int act, float scale, float* out_f32, void* out_hi,
+                    void* out_lo, cudaStream_t stream);
+size_t sc_clip_workspace_bytes(const ScClipConfig* cfg, int batch);
+/* images [B,3,S,S] fp32 (already CLIP-normalised) -> emb [B,out_dim] L2-normalised fp32 (+ optional unnormalised copy and
+ * hi/lo bf16 planes of the normalised embedding for sc_cosine_topk). */
+int sc_clip_encode(const ScClipConfig* cfg, const ScClipWeights* weights, const float* images, int batch,
+                   float* emb, float* emb_unnormalised, void* emb_hi, void* emb_lo, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
+/* values/indices [n_query,k]: the k largest cosine similarities of each query against the first n_bank_valid rows of
+ * the bank (ties: lowest index). sim_workspace: fp32 [n_query, n_bank]. n_bank (allocated rows) % 64 == 0, dim % 64 == 0. */
+int sc_cosine_topk(const void* q_hi, const void* q_lo, const void* bank_hi, const void* bank_lo, int n_query,
+                   int n_bank, int n_bank_valid, int dim, int k, float* sim_workspace, float* values,
+                   int32_t* indices, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

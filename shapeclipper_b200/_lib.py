@@ -44,8 +44,9 @@ def _declare(L):
     L.sc_chamfer_forward.restype = i
     L.sc_chamfer_backward.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, vp]
     L.sc_chamfer_backward.restype = i
-    from . import _render_native
+    from . import _render_native, clip
     _render_native.declare(L)
+    clip.declare(L)
 
 
 def ptr(t):

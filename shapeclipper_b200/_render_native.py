@@ -74,13 +74,27 @@ def pack_weights(weights, biases):
 
 
 _blob_cache = {}
+_uid_counter = [0]
+
+
+def _uid(t):
+    """Identity of a parameter object that is never recycled (data_ptr / id() are, by the caching allocator / GC)."""
+    u = getattr(t, "_sc_uid", None)
+    if u is None:
+        _uid_counter[0] += 1
+        u = _uid_counter[0]
+        try:
+            t._sc_uid = u
+        except Exception:  # noqa: BLE001 - tensors that cannot carry attributes are simply never cached
+            return -_uid_counter[0]
+    return u
 
 
 def packed_blob(weights, biases):
     """pack_weights with a small cache keyed on (storage, version) of every tensor: the kernel calls of one
     training step share one packing per parameter set. In-place updates through autograd-visible ops (optimisers,
     load_state_dict) bump the version; after raw `.data` writes call invalidate_blob_cache()."""
-    key = tuple((t.data_ptr(), t._version) for t in list(weights) + list(biases))
+    key = tuple((_uid(t), t.data_ptr(), t._version) for t in list(weights) + list(biases))
     dev = str(weights[0].device)
     cache = _blob_cache.setdefault(dev, {})
     blob = cache.get(key)

@@ -1,0 +1,298 @@
+"""CLIP ViT image tower + cosine k-NN on the sm_100a kernels, behind the call surface the reference uses:
+
+    model, preprocess = clip.load("ViT-L/14", device)          (CLIP_anno.py:16)
+    emb = model.encode_image(images).float()                    (CLIP_anno.py:166)
+    indices, values = calc_matches(features, k_nearest=6)       (CLIP_anno.py:29-57, opt.thres = None)
+
+Parameters carry openai/CLIP's `visual.*` names and shapes so real checkpoints load 1:1; without a checkpoint
+(no network in this environment) the tower is random-initialised with CLIP's init scales.
+GEMMs: tcgen05 tensor cores; `precision="split"` (default) feeds hi/lo bf16 operand pairs (3 MMAs per product,
+fp32-class accuracy), `precision="bf16"` is the plain-bf16 throughput mode.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+CONFIGS = {
+    "ViT-B/32": dict(image_size=224, patch=32, width=768, layers=12, heads=12, out_dim=512),
+    "ViT-L/14": dict(image_size=224, patch=14, width=1024, layers=24, heads=16, out_dim=768),
+    "tiny": dict(image_size=64, patch=32, width=128, layers=2, heads=2, out_dim=64),
+}
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+_vp = ctypes.c_void_p
+
+
+class ScClipConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("image_size", "patch", "width", "layers", "heads", "out_dim", "split")]
+
+
+class ScClipLayer(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("ln1_w", "ln1_b", "qkv_w_hi", "qkv_w_lo", "qkv_b", "out_w_hi", "out_w_lo", "out_b",
+                                   "ln2_w", "ln2_b", "fc1_w_hi", "fc1_w_lo", "fc1_b", "fc2_w_hi", "fc2_w_lo", "fc2_b")]
+
+
+class ScClipWeights(ctypes.Structure):
+    _fields_ = [(n, _vp) for n in ("conv_w_hi", "conv_w_lo", "class_emb", "pos_emb", "lnpre_w", "lnpre_b", "lnpost_w",
+                                   "lnpost_b", "proj_w_hi", "proj_w_lo")] + [("layers", ctypes.POINTER(ScClipLayer))]
+
+
+def declare(L):
+    i, sz, f = ctypes.c_int, ctypes.c_size_t, ctypes.c_float
+    L.sc_gemm_bf16_tc.argtypes = [_vp, _vp, _vp, _vp, i, i, i, _vp, _vp, i, f, _vp, _vp, _vp, _vp]
+    L.sc_gemm_bf16_tc.restype = i
+    L.sc_clip_workspace_bytes.argtypes = [ctypes.POINTER(ScClipConfig), i]
+    L.sc_clip_workspace_bytes.restype = sz
+    L.sc_clip_encode.argtypes = [ctypes.POINTER(ScClipConfig), ctypes.POINTER(ScClipWeights), _vp, i, _vp, _vp, _vp, _vp,
+                                 _vp, sz, _vp]
+    L.sc_clip_encode.restype = i
+    L.sc_cosine_topk.argtypes = [_vp, _vp, _vp, _vp, i, i, i, i, i, _vp, _vp, _vp, _vp]
+    L.sc_cosine_topk.restype = i
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def split_bf16(t):
+    """fp32 tensor -> (hi, lo) bf16 planes with hi + lo == t to ~2^-16 relative."""
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
+def gemm(a_hi, a_lo, w_hi, w_lo, bias=None, residual=None, act=0, scale=1.0, out_f32=True, out_split=False):
+    """Thin front of sc_gemm_bf16_tc (used by the tests): C = A W^T ... on tcgen05."""
+    L = _lib.lib()
+    M, K = a_hi.shape
+    N = w_hi.shape[0]
+    dev = a_hi.device
+    of = torch.empty(M, N, device=dev) if out_f32 else None
+    oh = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if out_split else None
+    ol = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if out_split else None
+    with torch.cuda.device(dev):
+        _lib.check(L.sc_gemm_bf16_tc(_p(a_hi), _p(a_lo), _p(w_hi), _p(w_lo), M, N, K, _p(bias), _p(residual), act, scale,
+                                     _p(of), _p(oh), _p(ol), _lib.stream_of(a_hi)), "sc_gemm_bf16_tc")
+    from . import _render_native as rn
+    rn.TIMERS.count()
+    return of, oh, ol
+
+
+class CLIPVisual(torch.nn.Module):
+    """The image half of a CLIP model (`model.visual` in openai/CLIP) — encode_image only, inference only."""
+
+    def __init__(self, name="ViT-B/32", precision="split", seed=0):
+        super().__init__()
+        self.name = name
+        self.cfg = dict(CONFIGS[name])
+        self.precision = precision
+        W, P, Ln = self.cfg["width"], self.cfg["patch"], self.cfg["layers"]
+        T = (self.cfg["image_size"] // P) ** 2 + 1
+        g = torch.Generator().manual_seed(seed)
+        s = W ** -0.5
+
+        def rn(*shape, std):
+            return torch.nn.Parameter(torch.randn(*shape, generator=g) * std, requires_grad=False)
+
+        def ones(n):
+            return torch.nn.Parameter(torch.ones(n), requires_grad=False)
+
+        def zeros(n):
+            return torch.nn.Parameter(torch.zeros(n), requires_grad=False)
+        P_ = self._parameters
+        P_["conv1.weight"] = rn(W, 3, P, P, std=(3 * P * P) ** -0.5)
+        P_["class_embedding"] = rn(W, std=s)
+        P_["positional_embedding"] = rn(T, W, std=s)
+        for nm in ("ln_pre", "ln_post"):
+            P_[nm + ".weight"], P_[nm + ".bias"] = ones(W), zeros(W)
+        P_["proj"] = rn(W, self.cfg["out_dim"], std=s)
+        for i in range(Ln):
+            b = "transformer.resblocks.%d." % i
+            P_[b + "ln_1.weight"], P_[b + "ln_1.bias"], P_[b + "ln_2.weight"], P_[b + "ln_2.bias"] = ones(W), zeros(W), ones(W), zeros(W)
+            P_[b + "attn.in_proj_weight"], P_[b + "attn.in_proj_bias"] = rn(3 * W, W, std=s), zeros(3 * W)
+            P_[b + "attn.out_proj.weight"], P_[b + "attn.out_proj.bias"] = rn(W, W, std=s * (2 * Ln) ** -0.5), zeros(W)
+            P_[b + "mlp.c_fc.weight"], P_[b + "mlp.c_fc.bias"] = rn(4 * W, W, std=(2 * W) ** -0.5), zeros(4 * W)
+            P_[b + "mlp.c_proj.weight"], P_[b + "mlp.c_proj.bias"] = rn(W, 4 * W, std=s * (2 * Ln) ** -0.5), zeros(W)
+        self._packed = None
+
+    # torch.nn.Module stores parameters by attribute name; dotted names only live in _parameters / state_dict
+    def load_params(self, params):
+        """params: dict with openai/CLIP `visual.` names (prefix optional)."""
+        with torch.no_grad():
+            for k, v in params.items():
+                k = k[len("visual."):] if k.startswith("visual.") else k
+                if k in self._parameters:
+                    self._parameters[k].copy_(v.to(self._parameters[k].dtype))
+        self._packed = None
+
+    def _pack(self):
+        if self._packed is not None:
+            return self._packed
+        P_ = self._parameters
+        dev = P_["proj"].device
+        _lib.require_cuda(P_["proj"])
+        keep = []
+        split = self.precision == "split"
+
+        def mat(t):
+            hi, lo = split_bf16(t.detach().float().contiguous())
+            keep.extend([hi, lo])
+            return _p(hi), (_p(lo) if split else None)
+
+        def vec(t):
+            v = t.detach().float().contiguous()
+            keep.append(v)
+            return _p(v)
+        W = self.cfg["width"]
+        layers = (ScClipLayer * self.cfg["layers"])()
+        for i in range(self.cfg["layers"]):
+            b = "transformer.resblocks.%d." % i
+            Lr = layers[i]
+            Lr.ln1_w, Lr.ln1_b, Lr.ln2_w, Lr.ln2_b = vec(P_[b + "ln_1.weight"]), vec(P_[b + "ln_1.bias"]), vec(P_[b + "ln_2.weight"]), vec(P_[b + "ln_2.bias"])
+            Lr.qkv_w_hi, Lr.qkv_w_lo = mat(P_[b + "attn.in_proj_weight"]); Lr.qkv_b = vec(P_[b + "attn.in_proj_bias"])
+            Lr.out_w_hi, Lr.out_w_lo = mat(P_[b + "attn.out_proj.weight"]); Lr.out_b = vec(P_[b + "attn.out_proj.bias"])
+            Lr.fc1_w_hi, Lr.fc1_w_lo = mat(P_[b + "mlp.c_fc.weight"]); Lr.fc1_b = vec(P_[b + "mlp.c_fc.bias"])
+            Lr.fc2_w_hi, Lr.fc2_w_lo = mat(P_[b + "mlp.c_proj.weight"]); Lr.fc2_b = vec(P_[b + "mlp.c_proj.bias"])
+        w = ScClipWeights()
+        conv = P_["conv1.weight"].reshape(W, -1)
+        kpad = (-conv.shape[1]) % 64                 # ViT-L/14: 3*14*14 = 588 -> 640 (the im2col kernel pads alike)
+        if kpad:
+            conv = torch.cat([conv, torch.zeros(W, kpad, device=conv.device, dtype=conv.dtype)], dim=1)
+        w.conv_w_hi, w.conv_w_lo = mat(conv)
+        w.class_emb, w.pos_emb = vec(P_["class_embedding"]), vec(P_["positional_embedding"])
+        w.lnpre_w, w.lnpre_b = vec(P_["ln_pre.weight"]), vec(P_["ln_pre.bias"])
+        w.lnpost_w, w.lnpost_b = vec(P_["ln_post.weight"]), vec(P_["ln_post.bias"])
+        w.proj_w_hi, w.proj_w_lo = mat(P_["proj"].t())
+        w.layers = ctypes.cast(layers, ctypes.POINTER(ScClipLayer))
+        cfg = ScClipConfig(split=1 if split else 0, **self.cfg)
+        self._packed = (cfg, w, layers, keep, dev)
+        return self._packed
+
+    @torch.no_grad()
+    def encode(self, images, want_planes=False):
+        """images [B,3,S,S] fp32 CUDA, CLIP-normalised -> (unnormalised emb, L2-normalised emb[, hi, lo planes])."""
+        cfg, w, _layers, _keep, dev = self._pack()
+        L = _lib.lib()
+        _lib.require_cuda(images)
+        img = images.float().contiguous()
+        B = img.shape[0]
+        D = self.cfg["out_dim"]
+        raw = torch.empty(B, D, device=dev); emb = torch.empty(B, D, device=dev)
+        hi = torch.empty(B, D, device=dev, dtype=torch.bfloat16) if want_planes else None
+        lo = torch.empty(B, D, device=dev, dtype=torch.bfloat16) if want_planes else None
+        with torch.cuda.device(dev):
+            nbytes = L.sc_clip_workspace_bytes(ctypes.byref(cfg), B)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            from . import _render_native as rn
+            with rn.TIMERS.span("clip_encode", dev):
+                _lib.check(L.sc_clip_encode(ctypes.byref(cfg), ctypes.byref(w), _p(img), B, _p(emb), _p(raw), _p(hi), _p(lo),
+                                            _p(ws), nbytes, _lib.stream_of(img)), "sc_clip_encode")
+            rn.TIMERS.count(5 + 7 * self.cfg["layers"] + 3)      # kernels launched by one encode
+        return (raw, emb, hi, lo) if want_planes else (raw, emb)
+
+    def encode_image(self, images):
+        """Same contract as clip_model.encode_image: the projected, NOT normalised, embedding."""
+        return self.encode(images)[0]
+
+
+class _Model:
+    """What `clip.load` returns first: an object with .encode_image (text tower is not part of the hot path)."""
+
+    def __init__(self, visual):
+        self.visual = visual
+
+    def encode_image(self, images):
+        return self.visual.encode_image(images)
+
+    def eval(self):
+        return self
+
+
+def preprocess(image_tensor, size=224):
+    """CLIP's image transform on a float tensor in [0,1] [..,3,h,w]: bicubic resize (short side), centre crop, normalise."""
+    import torch.nn.functional as F
+    x = image_tensor
+    h, w = x.shape[-2:]
+    sc = size / min(h, w)
+    nh, nw = max(size, round(h * sc)), max(size, round(w * sc))
+    x = F.interpolate(x.reshape(-1, 3, h, w), size=(nh, nw), mode="bicubic", align_corners=False, antialias=True)
+    t, l = (nh - size) // 2, (nw - size) // 2
+    x = x[..., t:t + size, l:l + size]
+    mean = torch.tensor(CLIP_MEAN, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_STD, device=x.device).view(1, 3, 1, 1)
+    return (x - mean) / std
+
+
+def load(name="ViT-L/14", device="cuda", precision="split", state_dict=None):
+    """clip.load equivalent for the image tower. state_dict: an openai/CLIP checkpoint's tensors (optional)."""
+    vis = CLIPVisual(name, precision=precision)
+    if state_dict is not None:
+        vis.load_params(state_dict)
+    return _Model(vis.to(device)), preprocess
+
+
+@torch.no_grad()
+def calc_matches(features, k_nearest=6, bank=None):
+    """Cosine k-NN of L2-normalised features [N,D] against themselves (or `bank`): (indices [N,k], values [N,k]).
+    NN_annotator.calc_matches with opt.thres = None; one tcgen05 GEMM + one top-k kernel instead of N GEMVs."""
+    L = _lib.lib()
+    _lib.require_cuda(features)
+    f = features.float().contiguous()
+    b = f if bank is None else bank.float().contiguous()
+    N, D = f.shape
+    Nb = b.shape[0]
+    pad = (-Nb) % 64
+    if pad:
+        b = torch.cat([b, torch.zeros(pad, D, device=b.device)], 0)
+    if D % 64:
+        raise ValueError("embedding dim must be a multiple of 64")
+    q_hi, q_lo = split_bf16(f)
+    b_hi, b_lo = split_bf16(b)
+    sim = torch.empty(N, b.shape[0], device=f.device)
+    val = torch.empty(N, k_nearest, device=f.device)
+    idx = torch.empty(N, k_nearest, dtype=torch.int32, device=f.device)
+    with torch.cuda.device(f.device):
+        _lib.check(L.sc_cosine_topk(_p(q_hi), _p(q_lo), _p(b_hi), _p(b_lo), N, b.shape[0], Nb, D, k_nearest, _p(sim), _p(val),
+                                    _p(idx), _lib.stream_of(f)), "sc_cosine_topk")
+    from . import _render_native as rn
+    rn.TIMERS.count(2)
+    return idx.long(), val
+
+
+class _BenchContext:
+    """CLIP leg of bench.py: encode the batch images (ViT-B/32, random init) and look up the 6 nearest of a 4096 bank."""
+
+    def __init__(self, opt, batch, device, bank_size=4096):
+        self.model = CLIPVisual("ViT-B/32", precision="split").to(device)
+        self.device = device
+        g = torch.Generator().manual_seed(7)
+        self.host_images = [torch.randn(batch, 3, 224, 224, generator=g).pin_memory() for _ in range(2)]
+        self.images = [t.to(device) for t in self.host_images]
+        bank = torch.nn.functional.normalize(torch.randn(bank_size, 512, generator=g), dim=-1).to(device)
+        self.bank_hi, self.bank_lo = split_bf16(bank)
+        self.sim = torch.empty(batch, bank_size, device=device)
+        self.val = torch.empty(batch, 6, device=device)
+        self.idx = torch.empty(batch, 6, dtype=torch.int32, device=device)
+        self.h2d_bytes = self.host_images[0].numel() * 4
+        self.i = 0
+
+    def h2d(self, i):
+        return self.host_images[i % 2].to(self.device, non_blocking=True)
+
+    def run(self, images=None):
+        from . import _render_native as rn
+        L = _lib.lib()
+        img = images if images is not None else self.images[self.i % 2]
+        self.i += 1
+        raw, emb, hi, lo = self.model.encode(img, want_planes=True)
+        with torch.cuda.device(self.device):
+            _lib.check(L.sc_cosine_topk(_p(hi), _p(lo), _p(self.bank_hi), _p(self.bank_lo), img.shape[0], self.bank_hi.shape[0],
+                                        self.bank_hi.shape[0], 512, 6, _p(self.sim), _p(self.val), _p(self.idx), _lib.stream_of(img)), "sc_cosine_topk")
+        rn.TIMERS.count(2)
+        return self.idx
+
+
+def bench_context(opt, batch, device):
+    return _BenchContext(opt, batch, device)

@@ -199,41 +199,54 @@ struct WeightPipe {
 // ---------------------------------------------------------------------------------------------------------
 // Register-tiled GEMM pieces. Lane l owns points 4l..4l+3 of the tile, warp w owns outputs 8w..8w+7.
 // acc[i][j] += sum_k A[k][4l+i] * W[k][8w+j]          (A: shared k-major plane, W: shared [K][64])
+__device__ __forceinline__ void gemm64_step(float (&acc)[4][8], const float* __restrict__ a, const float* __restrict__ w, int k)
+{
+    const float4 p = *reinterpret_cast<const float4*>(a + k * LD);
+    const float4 w0 = *reinterpret_cast<const float4*>(w + k * HID);
+    const float4 w1 = *reinterpret_cast<const float4*>(w + k * HID + 4);
+    const float av[4] = {p.x, p.y, p.z, p.w};
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+}
+// The k loop is kept a REAL loop (4 steps per trip): fully unrolled, the ~50 GEMM call sites of the backward kernel
+// make >0.5 MB of straight-line SASS and the SM stalls on instruction fetch (ncu: stall_no_inst 36 % of samples).
 __device__ __forceinline__ void gemm64(float (&acc)[4][8], const float* __restrict__ A, int K,
                                        const float* __restrict__ W, int lane, int warp)
 {
     const float* a = A + 4 * lane;
     const float* w = W + 8 * warp;
-#pragma unroll 8
-    for (int k = 0; k < K; ++k) {
-        const float4 p = *reinterpret_cast<const float4*>(a + k * LD);
-        const float4 w0 = *reinterpret_cast<const float4*>(w + k * HID);
-        const float4 w1 = *reinterpret_cast<const float4*>(w + k * HID + 4);
-        const float av[4] = {p.x, p.y, p.z, p.w};
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    const int K4 = K & ~3;
+#pragma unroll 1
+    for (int k = 0; k < K4; k += 4) {
+        gemm64_step(acc, a, w, k); gemm64_step(acc, a, w, k + 1); gemm64_step(acc, a, w, k + 2); gemm64_step(acc, a, w, k + 3);
     }
+#pragma unroll 1
+    for (int k = K4; k < K; ++k) gemm64_step(acc, a, w, k);
 }
 // 40-wide output (39 used): warp w owns outputs 5w..5w+4.  W: shared [K=64][40]
+__device__ __forceinline__ void gemm40_step(float (&acc)[4][5], const float* __restrict__ a, const float* __restrict__ w, int k)
+{
+    const float4 p = *reinterpret_cast<const float4*>(a + k * LD);
+    const float av[4] = {p.x, p.y, p.z, p.w};
+    float wv[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) wv[j] = w[k * NPE_PAD + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+}
 __device__ __forceinline__ void gemm40(float (&acc)[4][5], const float* __restrict__ A, int K,
                                        const float* __restrict__ W, int lane, int warp)
 {
     const float* a = A + 4 * lane;
     const float* w = W + 5 * warp;
-#pragma unroll 8
-    for (int k = 0; k < K; ++k) {
-        const float4 p = *reinterpret_cast<const float4*>(a + k * LD);
-        const float av[4] = {p.x, p.y, p.z, p.w};
-        float wv[5];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) wv[j] = w[k * NPE_PAD + j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 5; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+#pragma unroll 1
+    for (int k = 0; k < K; k += 4) {
+        gemm40_step(acc, a, w, k); gemm40_step(acc, a, w, k + 1); gemm40_step(acc, a, w, k + 2); gemm40_step(acc, a, w, k + 3);
     }
 }
 
@@ -317,6 +330,7 @@ __device__ __forceinline__ void wgrad(const float* __restrict__ L, const float* 
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int b = 0; b < NRB; ++b) d[a][b] = 0.f;
+#pragma unroll 1
     for (int p = 0; p < npts; p += 4) {
         float4 l[4], r[NRB];
 #pragma unroll
