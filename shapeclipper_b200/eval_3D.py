@@ -1,0 +1,79 @@
+"""3-D evaluation pieces on the GPU path, with the reference's function names (utils/eval_3D.py):
+get_dense_3D_grid (9-18), compute_level_grid (21-38), normalize_pc (40-49), compute_fscore (105-121),
+chamfer_distance (155-165). Marching cubes + mesh sampling (convert_to_explicit, 123-153) are CPU third-party code
+(PyMCubes, trimesh) and stay outside: eval_metrics takes the predicted point cloud from a caller-supplied sampler."""
+import torch
+
+from . import chamfer_3D
+
+
+@torch.no_grad()
+def get_dense_3D_grid(opt, var, N=None):
+    batch_size = len(var.idx)
+    N = N or opt.eval.vox_res
+    lo, hi = opt.eval.range
+    g = torch.linspace(lo, hi, N + 1, device=opt.device)
+    pts = torch.stack(torch.meshgrid(g, g, g, indexing="ij"), dim=-1)        # [N+1, N+1, N+1, 3]
+    return pts.unsqueeze(0).expand(batch_size, -1, -1, -1, -1)
+
+
+@torch.no_grad()
+def compute_level_grid(opt, sdf_network, proj_latent_sdf, points_3D):
+    """SDF on the whole lattice in ONE point-mode kernel launch (the reference loops over N+1 slices)."""
+    B, n = points_3D.shape[0], points_3D.shape[1]
+    flat = points_3D.reshape(B, -1, 3).reshape(-1, 3).contiguous()
+    sdf = sdf_network.get_conditional_output(opt, B, flat, proj_latent_sdf, compute_grad=False)[0]
+    return sdf.view(B, n, n, n)
+
+
+@torch.no_grad()
+def normalize_pc(pc):
+    assert pc.dim() == 3
+    c = pc - pc.mean(dim=1, keepdim=True)
+    ext_x = c[:, :, 0].amax(-1) - c[:, :, 0].amin(-1)
+    ext_y = c[:, :, 1].amax(-1) - c[:, :, 1].amin(-1)
+    return c / (torch.maximum(ext_x, ext_y)[:, None, None] + 1.e-7)
+
+
+def compute_fscore(dist1, dist2, thresholds=(0.005, 0.01, 0.02, 0.05, 0.1, 0.2)):
+    cols = []
+    for th in thresholds:
+        precision = (dist1 < th).float().mean(dim=1)
+        recall = (dist2 < th).float().mean(dim=1)
+        f = 2 * precision * recall / (precision + recall)
+        cols.append(torch.where(torch.isnan(f), torch.zeros_like(f), f))
+    return torch.stack(cols, dim=1)
+
+
+def chamfer_distance(opt, X1, X2):
+    B, N1, N2 = len(X1), X1.shape[1], X2.shape[1]
+    assert X1.shape[2] == 3
+    dev = X1.device
+    d1 = torch.zeros(B, N1, device=dev); d2 = torch.zeros(B, N2, device=dev)
+    i1 = torch.zeros(B, N1, dtype=torch.int32, device=dev); i2 = torch.zeros(B, N2, dtype=torch.int32, device=dev)
+    if chamfer_3D.forward(X1, X2, d1, d2, i1, i2) != 1:
+        raise RuntimeError("chamfer_3D.forward failed")
+    return d1.sqrt(), d2.sqrt(), i1, i2
+
+
+@torch.no_grad()
+def eval_metrics(opt, var, sdf_network, surface_sampler, vis_only=False):
+    """utils/eval_3D.py:52-103 with the mesh extraction injected: surface_sampler(level_vox [B,n,n,n]) -> [B,P,3]."""
+    pts = get_dense_3D_grid(opt, var)
+    B = pts.shape[0]
+    level = compute_level_grid(opt, sdf_network, var.proj_latent_sdf, pts)
+    var.eval_vox = pts.reshape(B, -1, 3)
+    var.dpc_pred = surface_sampler(level).to(pts.device).float()
+    R_pred, R_gt = var.pose[..., :3], var.pose_gt[..., :3]
+    pred = (R_pred @ var.dpc_pred.transpose(1, 2)).transpose(1, 2)
+    gt = (R_gt @ var.dpc.points.transpose(1, 2)).transpose(1, 2)
+    if opt.data.dataset == "pix3d":
+        pred = pred * torch.tensor([1., -1., -1.], device=pred.device)
+        gt = gt * torch.tensor([-1., 1., 1.], device=gt.device)
+    var.dpc_pred, var.dpc.points = normalize_pc(pred.contiguous()), normalize_pc(gt.contiguous())
+    if vis_only:
+        return
+    dist_acc, dist_comp, _, _ = chamfer_distance(opt, var.dpc_pred, var.dpc.points)
+    var.f_score = compute_fscore(dist_acc, dist_comp, opt.eval.f_thresholds)
+    var.cd_acc, var.cd_comp = dist_acc.mean(dim=1), dist_comp.mean(dim=1)
+    return dist_acc.mean(), dist_comp.mean()

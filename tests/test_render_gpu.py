@@ -204,3 +204,27 @@ def test_sdf_query_backward_first_order_only():
     _close(s, s_ref, "sdf")
     for k, a, b in zip(["z", "pts"] + list(sp.keys()), got, ref):
         _grad_close(a, b, k, 1e-3)
+
+
+def test_level_grid_matches_oracle():
+    """E1: the (N+1)^3 SDF lattice of utils/eval_3D.py:9-38 in one launch vs the oracle's slice loop."""
+    from shapeclipper_b200 import eval_3D, options
+    from shapeclipper_b200.implicit import SDFNetwork
+    torch.manual_seed(31)
+    opt = options.default_options()
+    opt.eval.vox_res = 20
+    net = SDFNetwork(opt)
+    with torch.no_grad():
+        for p in net.parameters():
+            p.add_(0.02 * torch.randn_like(p))
+    z = torch.randn(2, 64) * 0.3
+    want = R.level_grid({k: v for k, v in net.state_dict().items()}, z, 20)
+    net = net.cuda()
+    var = options.Options(idx=torch.arange(2))
+    pts = eval_3D.get_dense_3D_grid(opt, var)
+    got = eval_3D.compute_level_grid(opt, net, z.cuda(), pts)
+    assert got.shape == (2, 21, 21, 21)
+    _close(got, want, "level grid")
+    d1, d2, _, _ = eval_3D.chamfer_distance(opt, pts.reshape(2, -1, 3)[:, :500].contiguous(), pts.reshape(2, -1, 3)[:, 100:900].contiguous())
+    f = eval_3D.compute_fscore(d1, d2)
+    assert f.shape == (2, 6) and torch.isfinite(f).all()
