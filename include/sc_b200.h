@@ -116,6 +116,15 @@ int sc_render_forward(const ScRenderArgs* args, cudaStream_t stream);
  * out_w/out_b = arrays of 10 device pointers (NULL entries are skipped), z_sdf_bar/z_rgb_bar [B,64],
  * beta_bar = d/d(|beta|+beta_min) (1 float). */
 int sc_render_backward(const ScRenderArgs* args, cudaStream_t stream);
+/* Tensor-core edition of the same kernels (tcgen05.mma on hi/lo bf16 operand pairs, accumulators in TMEM; same
+ * ScRenderArgs, same outputs to ~1e-5). args->blob must then be the blob of sc_render_tc_pack_weights and args->scratch
+ * sc_render_tc_scratch_bytes() bytes; cb / grad_partial / cb_bar and sc_render_grad_finalize are shared. */
+size_t sc_render_tc_blob_bytes(void);
+size_t sc_render_tc_scratch_bytes(int backward);
+int sc_render_tc_pack_weights(const float* const* w, const float* const* b, const float* ffma_blob, void* tc_blob,
+                              cudaStream_t stream);
+int sc_render_tc_forward(const ScRenderArgs* args, cudaStream_t stream);
+int sc_render_tc_backward(const ScRenderArgs* args, cudaStream_t stream);
 int sc_render_grad_finalize(const float* grad_partial, int n_ctas, const float* cb_bar, const float* z_sdf,
                             const float* z_rgb, const float* blob, int batch, float* const* out_w,
                             float* const* out_b, float* z_sdf_bar, float* z_rgb_bar, float* beta_bar,

@@ -40,6 +40,16 @@ def declare(L):
     L.sc_render_latent_bias.restype = i
     L.sc_render_forward.argtypes = [ctypes.POINTER(ScRenderArgs), vp]
     L.sc_render_forward.restype = i
+    L.sc_render_tc_blob_bytes.restype = sz
+    L.sc_render_tc_scratch_bytes.argtypes = [i]
+    L.sc_render_tc_scratch_bytes.restype = sz
+    L.sc_render_tc_pack_weights.argtypes = [vp, vp, vp, vp, vp]
+    L.sc_render_tc_pack_weights.restype = i
+    L.sc_render_tc_forward.argtypes = [ctypes.POINTER(ScRenderArgs), vp]
+    L.sc_render_tc_forward.restype = i
+    if hasattr(L, "sc_render_tc_backward"):
+        L.sc_render_tc_backward.argtypes = [ctypes.POINTER(ScRenderArgs), vp]
+        L.sc_render_tc_backward.restype = i
     if hasattr(L, "sc_render_backward"):
         L.sc_render_backward.argtypes = [ctypes.POINTER(ScRenderArgs), vp]
         L.sc_render_backward.restype = i
@@ -108,6 +118,33 @@ def packed_blob(weights, biases):
 
 def invalidate_blob_cache():
     _blob_cache.clear()
+    _tc_blob_cache.clear()
+
+
+_tc_blob_cache = {}
+
+
+def packed_tc_blob(weights, biases, ffma_blob):
+    """The tensor-core blob (swizzled hi/lo bf16 weight tiles) for the same parameter set, cached like packed_blob."""
+    L = _lib.lib()
+    key = tuple((_uid(t), t.data_ptr(), t._version) for t in list(weights) + list(biases))
+    dev = weights[0].device
+    cache = _tc_blob_cache.setdefault(str(dev), {})
+    blob = cache.get(key)
+    if blob is None:
+        if len(cache) >= 4:
+            cache.clear()
+        ws = [_f32c(w.detach()) for w in weights]
+        bs = [_f32c(b.detach()) for b in biases]
+        blob = torch.empty(L.sc_render_tc_blob_bytes(), dtype=torch.uint8, device=dev)
+        warr = (ctypes.c_void_p * 10)(*[w.data_ptr() for w in ws])
+        barr = (ctypes.c_void_p * 10)(*[b.data_ptr() for b in bs])
+        with torch.cuda.device(dev):
+            _lib.check(L.sc_render_tc_pack_weights(warr, barr, _p(ffma_blob), _p(blob), _lib.stream_of(blob)),
+                       "sc_render_tc_pack_weights")
+        TIMERS.count()
+        cache[key] = blob
+    return blob
 
 
 def latent_bias(blob, z_sdf, z_rgb, batch):
@@ -122,10 +159,10 @@ def latent_bias(blob, z_sdf, z_rgb, batch):
     return cb
 
 
-def scratch(device, backward):
+def scratch(device, backward, tc=False):
     L = _lib.lib()
     with torch.cuda.device(device):
-        n = L.sc_render_scratch_bytes(1 if backward else 0)
+        n = (L.sc_render_tc_scratch_bytes if tc else L.sc_render_scratch_bytes)(1 if backward else 0)
     return torch.empty(n // 4, dtype=torch.float32, device=device)
 
 
@@ -174,19 +211,21 @@ class _Span:
 TIMERS = KernelTimers()
 
 
-def launch_forward(args, device):
+def launch_forward(args, device, tc=False):
     L = _lib.lib()
     with torch.cuda.device(device):
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         with TIMERS.span("render_fwd" if args.mode == 0 else "sdf_query_fwd", device):
-            _lib.check(L.sc_render_forward(ctypes.byref(args), stream), "sc_render_forward")
+            fn = L.sc_render_tc_forward if tc else L.sc_render_forward
+            _lib.check(fn(ctypes.byref(args), stream), "sc_render_tc_forward" if tc else "sc_render_forward")
     TIMERS.count()
 
 
-def launch_backward(args, device):
+def launch_backward(args, device, tc=False):
     L = _lib.lib()
     with torch.cuda.device(device):
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         with TIMERS.span("render_bwd" if args.mode == 0 else "sdf_query_bwd", device):
-            _lib.check(L.sc_render_backward(ctypes.byref(args), stream), "sc_render_backward")
+            fn = L.sc_render_tc_backward if tc else L.sc_render_backward
+            _lib.check(fn(ctypes.byref(args), stream), "sc_render_tc_backward" if tc else "sc_render_backward")
     TIMERS.count()

@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "_obj")
 LIB = os.path.join(PKG, "libsc_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+FLAGS = (["-DSC_TC_TRACE"] if os.environ.get("SC_TC_TRACE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
 

@@ -1,0 +1,251 @@
+// render_tc.cuh — tensor-core (tcgen05 / TMEM) edition of the fused render kernels: shared definitions.
+//
+// Same tile program as render_tile.cuh (128 sample points per tile, one persistent CTA per SM), but every
+// [128 x 64 x 64] layer GEMM is a burst of tcgen05.mma (UMMA 128x64x16) with the accumulator in TMEM, and every
+// weight-gradient GEMM (contraction over the tile's 128 points) is a UMMA 64x64x16 whose accumulator STAYS in TMEM
+// for the whole kernel (12 matrices interleaved in 384 columns) — no per-tile flush.
+// FP32-class accuracy on bf16 tensor cores: every operand is a hi/lo bf16 pair, every product 3 MMAs
+//      (Ah + Al)(Wh + Wl) ~= Ah Wh + Ah Wl + Al Wh          (2^-17 relative operand error; tf32 would be 2^-11)
+//
+// Shared-memory operand format: one "plane" = [128 rows (points)] x [64 bf16 = 128 B], 16-byte chunks XOR-swizzled with
+// (row & 7) (the SWIZZLE_128B image TMA produces). The SAME bytes serve as
+//   * K-major A operand of a layer GEMM      (M = point, K = feature), and
+//   * MN-major A/B operand of a weight-grad  (M/N = feature, K = point).
+// Thread mapping of the 512 threads: TMEM lane / point row r = 32*(warp & 3) + lane, column group ch = warp >> 2
+// (columns 16 ch .. 16 ch + 15) — what tcgen05.ld.32x32b.x16 delivers. 16 warps hide the MMA / L2 latencies of the
+// strictly serial phase chain far better than 8 (ncu: 8-warp version 15 % issue-active, 37 % long-scoreboard stalls).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_tc.cuh"
+#include "render_common.cuh"
+#include "sc_b200.h"
+
+namespace sct {
+
+using scr::HID; using scr::NPE; using scr::M_TILE;
+
+constexpr int kThreads = 512;                     // 16 warps: TMEM lane quarter = warp & 3, column group = warp >> 2
+constexpr int NC = 16;                            // accumulator columns per thread
+constexpr int kPlaneBytes = 128 * 128;            // one bf16 plane of a [128 x 64] tile
+constexpr int kActBytes = 2 * kPlaneBytes;        // hi + lo
+constexpr int kWPlaneBytes = 64 * 128;            // weight tile [64 x 64] bf16
+constexpr int kWSegBytes = 2 * kWPlaneBytes;      // hi + lo = 16 KB
+constexpr int kNumAct = 5;                        // P X Y Z U (the forward kernel uses 4)
+constexpr int kWSlots = 4;                        // weight ring depth of the forward kernel (prefetch distance 3)
+
+// ---- packed weight blob (bytes): 24 swizzled bf16 hi/lo segments, then the fp32 const + latent regions of the FFMA blob
+enum SegTC : int {
+    A0N = 0, B1N, A1N, B2N, A2N, W3N, W4N, W5FN, V0PN, V0FN, V1N, V2N,       // rows = out, cols = in  (y = W x)
+    W4T, W3T, B2T, B1T, A2T, A1T, A0T, W5FT, V2T, V1T, V0FT, V0PT,          // rows = in, cols = out  (x_bar = W^T y_bar)
+    NSEG_TC
+};
+constexpr size_t kSegRegionBytes = (size_t)NSEG_TC * kWSegBytes;             // 393 216
+constexpr size_t kTcConstOffsetBytes = kSegRegionBytes;                      // fp32 consts (scr::kConstFloats)
+constexpr size_t kTcLatentOffsetBytes = kTcConstOffsetBytes + (size_t)scr::kConstFloats * 4;
+constexpr size_t kTcBlobBytes = kTcLatentOffsetBytes + (size_t)scr::kLatentFloats * 4;
+
+// ---- TMEM columns
+constexpr uint32_t TM_ACC0 = 0, TM_ACC1 = 64, TM_WGRAD = 128;               // 12 weight-grad matrices, 2 per 64 columns
+enum WG : int { WG_A0 = 0, WG_A1, WG_A2, WG_B1, WG_B2, WG_W3, WG_W4, WG_W5F, WG_V0P, WG_V0F, WG_V1, WG_V2, NWG };
+__device__ __forceinline__ uint32_t wg_taddr(uint32_t tmem_base, int m) {     // matrix m: columns 128 + 64 (m/2), lanes +16 (m&1)
+    return tmem_base + TM_WGRAD + 64u * (uint32_t)(m >> 1) + ((uint32_t)((m & 1) * 16) << 16);
+}
+
+// ---- shared-memory map (bytes; the dynamic buffer is aligned to 1024 in the kernel)
+// forward kernel: 4 activation buffers + 4 weight slots; backward kernel: 5 + 2 (both 192 KB)
+constexpr int SMB_ACT = 0;
+constexpr int SMB_W_FWD = SMB_ACT + 4 * kActBytes;                    // forward: weight slots start here
+constexpr int SMB_W_BWD = SMB_ACT + 5 * kActBytes;                    // backward
+constexpr int SMB_F32 = SMB_ACT + 6 * kActBytes;                      // float area (after 192 KB of operands)
+constexpr int SF_CONST = 0;
+constexpr int SF_CB = SF_CONST + scr::kConstFloats;
+constexpr int SF_BIAS = SF_CB + 256;                                   // [8][64] per-tile bias tables
+constexpr int SF_PT = SF_BIAS + 512;
+constexpr int kPtVecsTc = scr::kPtVecs + 16;                          // + 4 scratch vectors x 4 column groups
+constexpr int SF_RAY = SF_PT + kPtVecsTc * M_TILE;                    // per-ray scratch (<= 32 rays): 704 floats
+constexpr int SF_VACC = SF_RAY + 704;                                 // backward: vector-gradient accumulators (588 floats)
+constexpr int SF_MISC = SF_VACC + 592;                                // seq[64] bytes, seq_len, wg_mask
+constexpr int SF_END = SF_MISC + 32;
+constexpr int SMB_BAR = SMB_F32 + SF_END * 4;                         // mbarriers: wfull[4] wfree[4] mma_done, tmem slot
+constexpr int kSmemBytesTc = SMB_BAR + 128;                           // all-dynamic, __align__(1024): no static smem, no slack
+static_assert(kSmemBytesTc <= 232448, "exceeds the 227 KB shared memory of one CTA");
+enum PtVecTc : int { PX_A = scr::kPtVecs, PX_B = PX_A + 4, PX_C = PX_B + 4, PX_D = PX_C + 4 };   // 4 scratch vectors x [4 column groups]
+
+// ---------------------------------------------------------------------------------------------------------
+// hi = bf16_rn(v), lo = bf16_rn(v - hi): hi + lo reproduces v to ~2^-17 relative. Two values per F2FP.
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    const float la = a - __uint_as_float(hi << 16), lb = b - __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 t = __floats2bfloat162_rn(la, lb);
+    lo = *reinterpret_cast<const uint32_t*>(&t);
+}
+
+// write NC consecutive columns (group ch) of row r into a hi/lo plane pair
+__device__ __forceinline__ void row_store(uint8_t* act, int r, int ch, const float (&v)[NC]) {
+    uint8_t* hi = act + r * 128;
+    uint8_t* lo = hi + kPlaneBytes;
+#pragma unroll
+    for (int q = 0; q < NC / 8; ++q) {
+        const int pos = ((ch * (NC / 8) + q) ^ (r & 7)) << 4;
+        uint4 h, l;
+        split_pair(v[q * 8 + 0], v[q * 8 + 1], h.x, l.x);
+        split_pair(v[q * 8 + 2], v[q * 8 + 3], h.y, l.y);
+        split_pair(v[q * 8 + 4], v[q * 8 + 5], h.z, l.z);
+        split_pair(v[q * 8 + 6], v[q * 8 + 7], h.w, l.w);
+        *reinterpret_cast<uint4*>(hi + pos) = h;
+        *reinterpret_cast<uint4*>(lo + pos) = l;
+    }
+}
+// read them back (hi + lo, ~2^-17 relative)
+__device__ __forceinline__ void row_load(const uint8_t* act, int r, int ch, float (&v)[NC]) {
+    const uint8_t* hi = act + r * 128;
+    const uint8_t* lo = hi + kPlaneBytes;
+#pragma unroll
+    for (int q = 0; q < NC / 8; ++q) {
+        const int pos = ((ch * (NC / 8) + q) ^ (r & 7)) << 4;
+        const uint4 h = *reinterpret_cast<const uint4*>(hi + pos);
+        const uint4 l = *reinterpret_cast<const uint4*>(lo + pos);
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+        const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 a = __bfloat1622float2(hp[e]), b = __bfloat1622float2(lp[e]);
+            v[q * 8 + 2 * e] = a.x + b.x; v[q * 8 + 2 * e + 1] = a.y + b.y;
+        }
+    }
+}
+// single element (row r, column c) of a plane pair
+__device__ __forceinline__ float act_elem(const uint8_t* act, int r, int c) {
+    const int off = r * 128 + ((((c >> 3) ^ (r & 7))) << 4) + ((c & 7) << 1);
+    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(act + off)) +
+           __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(act + kPlaneBytes + off));
+}
+
+// global stash planes (128 x 64 fp32): only ever re-read by the thread that wrote them, so the layout is chosen for
+// coalescing: float4 index (ch * NC/4 + q) * 128 + row — consecutive lanes (rows) are consecutive 16-byte words.
+__device__ __forceinline__ void st_store(float* plane, int r, int ch, const float (&v)[NC]) {
+    float4* p = reinterpret_cast<float4*>(plane) + (ch * (NC / 4)) * 128 + r;
+#pragma unroll
+    for (int q = 0; q < NC / 4; ++q) __stcg(p + q * 128, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+}
+__device__ __forceinline__ void st_load(const float* plane, int r, int ch, float (&v)[NC]) {
+    const float4* p = reinterpret_cast<const float4*>(plane) + (ch * (NC / 4)) * 128 + r;
+#pragma unroll
+    for (int q = 0; q < NC / 4; ++q) { const float4 t = __ldcg(p + q * 128); v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w; }
+}
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float (&v)[NC]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+constexpr int kStashPlane = 128 * 64;     // floats per stash plane
+
+// ---- UMMA descriptors for this layout
+// K-major (layer GEMMs): rows of 128 B, 8-row groups 1024 B apart — identical to gemm_tc.cuh::make_smem_desc_k128
+// MN-major (weight-grad GEMMs): MN = the 64 features of one 128-B row, K = rows; 8-row groups 1024 B apart (SBO)
+__device__ __forceinline__ uint64_t make_smem_desc_mn128(const void* tile) {
+    uint64_t d = 0;
+    d |= (uint64_t)((sctc::smem_u32(tile) >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024 >> 4) << 16;                          // LBO: next 64-wide MN group (unused: MN = 64)
+    d |= (uint64_t)(1024 >> 4) << 32;                          // SBO: next group of 8 K rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                                    // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {     // both operands MN-major
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[128 x 64] (+)= ACT[128 x 64] . W^T   (3 MMAs per 16-wide k-step). Issued by ONE thread.
+__device__ __forceinline__ void issue_layer_gemm(uint32_t tmem_d, const uint8_t* act, const uint8_t* w, bool accumulate) {
+    constexpr uint32_t idesc = sctc::make_idesc_bf16(128, 64);
+    const uint64_t ah = sctc::make_smem_desc_k128(act), al = sctc::make_smem_desc_k128(act + kPlaneBytes);
+    const uint64_t wh = sctc::make_smem_desc_k128(w), wl = sctc::make_smem_desc_k128(w + kWPlaneBytes);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint64_t adv = (uint64_t)(2 * k);
+        sctc::umma_bf16(tmem_d, ah + adv, wh + adv, idesc, (accumulate || k > 0) ? 1u : 0u);
+        sctc::umma_bf16(tmem_d, ah + adv, wl + adv, idesc, 1u);
+        sctc::umma_bf16(tmem_d, al + adv, wh + adv, idesc, 1u);
+    }
+}
+// D[64 x 64] += L^T . R over the tile's 128 points (L, R = plane pairs). Issued by ONE thread.
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, const uint8_t* L, const uint8_t* R, bool accumulate) {
+    constexpr uint32_t idesc = make_idesc_bf16_mn(64, 64);
+    const uint64_t lh = make_smem_desc_mn128(L), ll = make_smem_desc_mn128(L + kPlaneBytes);
+    const uint64_t rh = make_smem_desc_mn128(R), rl = make_smem_desc_mn128(R + kPlaneBytes);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint64_t adv = (uint64_t)(k * (16 * 128 >> 4));          // 16 points = 16 rows of 128 B
+        sctc::umma_bf16(tmem_d, lh + adv, rh + adv, idesc, (accumulate || k > 0) ? 1u : 0u);
+        sctc::umma_bf16(tmem_d, lh + adv, rl + adv, idesc, 1u);
+        sctc::umma_bf16(tmem_d, ll + adv, rh + adv, idesc, 1u);
+    }
+}
+
+// ---- weight ring: NS slots, TMA-filled (wfull), released by tcgen05.commit (wfree). Prefetch distance NS - 1:
+// a 16 KB bulk copy from L2 takes ~1-2 k cycles, longer than one tensor-core layer phase.
+struct WeightRing {
+    const uint8_t* blob;
+    uint8_t* slots;
+    uint64_t *wfull, *wfree;      // [NS] each
+    const int8_t* seq;
+    int seq_len;
+    int NS;
+    uint32_t n;                   // matrices consumed
+    int pos_fetch;                // position in seq of the next matrix to fetch
+
+    __device__ __forceinline__ void issue(uint32_t idx) {
+        const uint32_t s = idx % (uint32_t)NS;
+        uint64_t* bar = wfull + s;
+        scr::mbar_expect_tx(bar, kWSegBytes);
+        scr::tma_bulk_g2s(slots + s * kWSegBytes, blob + (size_t)seq[pos_fetch] * kWSegBytes, kWSegBytes, bar);
+        pos_fetch = (pos_fetch + 1 == seq_len) ? 0 : pos_fetch + 1;
+    }
+    __device__ __forceinline__ void prologue() {
+        n = 0; pos_fetch = 0;
+        if (threadIdx.x == 0) for (int i = 0; i < NS - 1; ++i) issue((uint32_t)i);
+    }
+    // all threads: publishes the operand stores of the previous epilogue to the async proxy, syncs the CTA and returns the
+    // slot of matrix n. Only thread 0 (the MMA issuer) waits for the weights to land.
+    __device__ __forceinline__ const uint8_t* acquire() {
+        sctc::fence_proxy_async();
+        sctc::tc_fence_before();
+        __syncthreads();
+        sctc::tc_fence_after();
+        const uint32_t cur = n;
+        if (threadIdx.x == 0) scr::mbar_wait(wfull + (cur % NS), (cur / NS) & 1);
+        n = cur + 1;
+        return slots + (cur % NS) * kWSegBytes;
+    }
+    // thread 0, AFTER issuing the MMAs that read the slot returned by the last acquire(): release that slot when they
+    // complete, then prefetch matrix n + NS - 2 into the slot of the matrix before it (waiting for ITS MMAs, which are
+    // ahead of ours in the tensor pipe, so the wait overlaps useful work instead of delaying the issue).
+    __device__ __forceinline__ void release() {
+        const uint32_t cur = n - 1;
+        sctc::umma_commit(wfree + (cur % NS));
+        const uint32_t nx = cur + (uint32_t)NS - 1;
+        if (cur >= 1) scr::mbar_wait(wfree + (nx % NS), ((nx / NS) - 1) & 1);
+        issue(nx);
+    }
+    // NS - 1 copies are always in flight: wait for them before the CTA exits
+    __device__ __forceinline__ void drain() {
+        if (threadIdx.x == 0)
+            for (uint32_t m = n; m < n + (uint32_t)NS - 1; ++m) scr::mbar_wait(wfull + (m % NS), (m / NS) & 1);
+        __syncthreads();
+    }
+};
+
+}  // namespace sct

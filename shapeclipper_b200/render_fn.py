@@ -9,6 +9,27 @@ from . import _render_native as rn
 
 _N_SDF, _N_RGB = 6, 4
 
+# Which generation of the render kernels runs: "tc" = tcgen05 tensor cores on hi/lo bf16 operand pairs (3 MMAs per
+# product, ~1e-5 relative), "fp32" = FP32 FFMA (the bit-for-bit-closest path). Both are CUDA kernels of this library.
+import os as _os
+PRECISION = {"forward": _os.environ.get("SC_RENDER_FORWARD", "tc"), "backward": _os.environ.get("SC_RENDER_BACKWARD", "tc")}
+
+
+def set_precision(forward=None, backward=None):
+    for k, v in (("forward", forward), ("backward", backward)):
+        if v is not None:
+            if v not in ("tc", "fp32"):
+                raise ValueError("precision must be 'tc' or 'fp32'")
+            PRECISION[k] = v
+
+
+def _fwd_tc():
+    return PRECISION["forward"] == "tc"
+
+
+def _bwd_tc():
+    return PRECISION["backward"] == "tc" and hasattr(_lib.lib(), "sc_render_tc_backward")
+
 
 def _params_of(sdf_net, rgb_net, device):
     ws = [l.weight for l in sdf_net.linears()]
@@ -77,16 +98,18 @@ class _RenderFn(torch.autograd.Function):
         rgb = torch.empty(B, R, 3, device=dev); normal = torch.empty(B, R, 3, device=dev)
         mask = torch.empty(B, R, 1, device=dev); mask_hard = torch.empty(B, R, 1, device=dev)
         depth = torch.empty(B, R, 1, device=dev)
-        scratch = rn.scratch(dev, backward=False)
+        tc = _fwd_tc()
+        scratch = rn.scratch(dev, backward=False, tc=tc)
         beta_c = f(beta_param).reshape(1)
+        kblob = rn.packed_tc_blob(ws, bs, blob) if tc else blob
         args = _new_args(mode=0, batch=B, n_per_image=R, n_samples=cfg["n_samples"], beta_min=cfg["beta_min"],
                          cam_dist=cfg["cam_dist"], half_range=cfg["half_range"], bg_color=cfg["bg_color"],
-                         normal_pow=cfg["normal_pow"], blob=blob, cb=cb, beta_param=beta_c, cam_loc=cam_loc,
+                         normal_pow=cfg["normal_pow"], blob=kblob, cb=cb, beta_param=beta_c, cam_loc=cam_loc,
                          ray_dirs=ray_dirs, depth_fac=depth_fac, scale_dist=scale_dist, t_vals=t_vals,
                          rgb=rgb, mask=mask, mask_hard=mask_hard, depth=depth, normal=normal, scratch=scratch)
         if jit is not None:
             args.jitter = ctypes.c_void_p(jit.data_ptr())
-        rn.launch_forward(args, dev)
+        rn.launch_forward(args, dev, tc=tc)
         ctx.cfg = cfg
         ctx.has_jitter = jit is not None
         ctx.save_for_backward(blob, cb, beta_c, cam_loc, ray_dirs, depth_fac, scale_dist, t_vals,
@@ -112,10 +135,12 @@ class _RenderFn(torch.autograd.Function):
         cb_bar = torch.zeros(B, 7, 64, device=dev)
         dirs_bar = torch.zeros(B, R, 3, device=dev); fac_bar = torch.zeros(B, R, device=dev)
         loc_bar = torch.zeros(B, 3, device=dev); sd_bar = torch.zeros(B, device=dev)
-        scratch = rn.scratch(dev, backward=True)
+        tc = _bwd_tc()
+        scratch = rn.scratch(dev, backward=True, tc=tc)
+        kblob = rn.packed_tc_blob(ws, bs, blob) if tc else blob
         args = _new_args(mode=0, batch=B, n_per_image=R, n_samples=cfg["n_samples"], beta_min=cfg["beta_min"],
                          cam_dist=cfg["cam_dist"], half_range=cfg["half_range"], bg_color=cfg["bg_color"],
-                         normal_pow=cfg["normal_pow"], blob=blob, cb=cb, beta_param=beta_c, cam_loc=cam_loc,
+                         normal_pow=cfg["normal_pow"], blob=kblob, cb=cb, beta_param=beta_c, cam_loc=cam_loc,
                          ray_dirs=ray_dirs, depth_fac=depth_fac, scale_dist=scale_dist, t_vals=t_vals,
                          grad_partial=partial, cb_bar=cb_bar, ray_dirs_bar=dirs_bar, depth_fac_bar=fac_bar,
                          cam_loc_bar=loc_bar, scale_dist_bar=sd_bar, scratch=scratch)
@@ -124,7 +149,7 @@ class _RenderFn(torch.autograd.Function):
         for name, t in (("rgb_bar", rgb_bar), ("mask_bar", mask_bar), ("depth_bar", depth_bar), ("normal_bar", normal_bar)):
             if t is not None:
                 setattr(args, name, ctypes.c_void_p(t.data_ptr()))
-        rn.launch_backward(args, dev)
+        rn.launch_backward(args, dev, tc=tc)
         gw, gb, z_sdf_bar, z_rgb_bar, beta_bar = _finalize(L, partial, n_ctas, cb_bar, z_sdf, z_rgb, blob, B, ws, bs, True)
         beta_param_bar = (beta_bar * torch.sign(beta_c)).reshape(())
         return (None, beta_param_bar, loc_bar, dirs_bar, fac_bar, sd_bar, z_sdf_bar, z_rgb_bar, None, None, *gw, *gb)
@@ -150,12 +175,14 @@ class _SDFQueryFn(torch.autograd.Function):
         pts = rn._f32c(points.detach())
         sdf = torch.empty(P, 1, device=dev); feat = torch.empty(P, 64, device=dev)
         grad = torch.empty(P, 3, device=dev) if want_grad else None
-        scratch = rn.scratch(dev, backward=False)
+        tc = _fwd_tc()
+        scratch = rn.scratch(dev, backward=False, tc=tc)
+        kblob = rn.packed_tc_blob(ws, bs, blob) if tc else blob
         args = _new_args(mode=1, batch=B, n_per_image=N, n_samples=1, want_grad=int(want_grad), want_feat=1,
-                         beta_min=1e-4, blob=blob, cb=cb, points=pts, sdf=sdf, feat=feat, scratch=scratch)
+                         beta_min=1e-4, blob=kblob, cb=cb, points=pts, sdf=sdf, feat=feat, scratch=scratch)
         if grad is not None:
             args.grad = ctypes.c_void_p(grad.data_ptr())
-        rn.launch_forward(args, dev)
+        rn.launch_forward(args, dev, tc=tc)
         ctx.meta = (B, N, want_grad, detach_latent)
         ctx.save_for_backward(blob, cb, pts, rn._f32c(z_sdf.detach()), *params)
         ctx.set_materialize_grads(False)
@@ -180,9 +207,11 @@ class _SDFQueryFn(torch.autograd.Function):
         partial = torch.empty(n_ctas, L.sc_render_grad_floats(), device=dev)
         cb_bar = torch.zeros(B, 7, 64, device=dev)
         pts_bar = torch.zeros(B * N, 3, device=dev)
-        scratch = rn.scratch(dev, backward=True)
+        tc = _bwd_tc()
+        scratch = rn.scratch(dev, backward=True, tc=tc)
+        kblob = rn.packed_tc_blob(ws, bs, blob) if tc else blob
         args = _new_args(mode=1, batch=B, n_per_image=N, n_samples=1, want_grad=int(want_grad and grad_bar is not None),
-                         want_feat=0, detach_latent=int(detach_latent), beta_min=1e-4, blob=blob, cb=cb, points=pts,
+                         want_feat=0, detach_latent=int(detach_latent), beta_min=1e-4, blob=kblob, cb=cb, points=pts,
                          grad_partial=partial, cb_bar=cb_bar, points_bar=pts_bar, scratch=scratch)
         if sdf_bar is not None:
             keep1 = rn._f32c(sdf_bar)
@@ -190,7 +219,7 @@ class _SDFQueryFn(torch.autograd.Function):
         if grad_bar is not None and want_grad:
             keep2 = rn._f32c(grad_bar)
             args.grad_bar = ctypes.c_void_p(keep2.data_ptr())
-        rn.launch_backward(args, dev)
+        rn.launch_backward(args, dev, tc=tc)
         gw, gb, z_sdf_bar, _, _ = _finalize(L, partial, n_ctas, cb_bar, z_sdf, None, blob, B, ws, bs, False)
         return (None, None, None, pts_bar, (None if detach_latent else z_sdf_bar), *gw[:6], *gb[:6])
 

@@ -9,6 +9,17 @@ import torch
 from oracle import render_ref as R
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True, params=["tc", "fp32"])
+def render_precision(request):
+    """Every test runs on both generations of the render kernels: "tc" (tcgen05 tensor cores on hi/lo bf16 operand pairs,
+    the default) and "fp32" (FP32 FFMA)."""
+    from shapeclipper_b200 import render_fn
+    old = dict(render_fn.PRECISION)
+    render_fn.set_precision(forward=request.param, backward=request.param)
+    yield request.param
+    render_fn.set_precision(forward=old["forward"], backward=old["backward"])
 REL = 1e-4
 # Unit normals of grazing rays are ill-conditioned: on the golden fixtures the reference's own fp32 result is 1.8e-4
 # (mask 2e-3) to 1.8e-3 (mask 1e-4) away from an fp64 evaluation of the same inputs (measured with
