@@ -29,6 +29,8 @@ UNIT = "images/s"
 FLOP_FWD_PER_POINT = 199424.0       # SURVEY.md §8d convention: 2*(40320 SDF + 40320 grad-SDF + 19072 RGB)
 FLOP_BWD_PER_POINT = 398848.0       # train fwd+bwd = 3x fwd  ->  backward kernel = 2x fwd
 GRAPH_PARAMS = 36800589             # parameters of the reference Graph (flat all-reduce size)
+RENDER_BWD_DRAM_BYTES = 2587338512  # dram__bytes_read.sum + dram__bytes_write.sum of one render_tc_bwd_kernel<0> launch at this shape
+                                    # (ncu --set full, profiles/r01_render_tc_bwd_ncu_summary.txt)
 
 
 def parse():
@@ -40,6 +42,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=16, help="images per GPU")
     ap.add_argument("--ref-batch", type=int, default=2, help="images per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
     return ap.parse_args()
 
 
@@ -166,6 +169,7 @@ def run_ours(a):
     import torch.distributed as tdist
     from shapeclipper_b200 import _render_native as rn, dist as scdist, options, synthetic
     from shapeclipper_b200.graph import HotPathGraph
+    from shapeclipper_b200.step import TrainStep
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback exists)")
@@ -174,13 +178,14 @@ def run_ours(a):
     torch.cuda.set_device(dev)
     opt = options.default_options(device=str(dev))
     opt.reg.device_sampling = True                  # neighbour draw stays on the GPU (no host sync in the step)
+    opt.render.device_rng = True                    # stratified jitter / eikonal samples from the CUDA generator
     torch.manual_seed(0)
     graph = HotPathGraph(opt).to(dev)
     params = list(graph.renderer.parameters())
     hot = sum(p.numel() for p in params)
     flat = scdist.FlatGradients(params, extra=(GRAPH_PARAMS - hot) if world > 1 else 0, device=dev)
     flat.broadcast_parameters()
-    optim = torch.optim.Adam(params, lr=1e-4, foreach=True)
+    optim = torch.optim.Adam(params, lr=1e-4, foreach=True, capturable=not a.eager)
     clip_ctx = None
     try:
         from shapeclipper_b200 import clip as scclip
@@ -188,22 +193,15 @@ def run_ours(a):
     except ImportError:
         clip_ctx = None
     batches = [synthetic.make_batch(opt, a.batch, seed=1000 * rank + i) for i in range(4)]
-    resident = [synthetic.to_device(b, dev)[0] for b in batches]
+    resident = [{k: t.to(dev) for k, t in b.items()} for b in batches]
     h2d_bytes = sum(t.numel() * t.element_size() for t in batches[0].values())
     if clip_ctx is not None:
         h2d_bytes += clip_ctx.h2d_bytes
 
-    def step(var, clip_images=None):
-        flat.zero()
-        for k in ("pose", "intr", "scale_dist", "proj_latent_sdf", "proj_latent_rgb"):
-            var[k].grad = None
-        if clip_ctx is not None:
-            clip_ctx.run(clip_images)
-        var, loss = graph(opt, var, training=True, get_loss=True)
-        loss["all"].backward()
-        flat.all_reduce()
-        optim.step()
-        return loss["all"]
+    rn.TIMERS.reset()
+    rn.TIMERS.enabled = True                        # kernel spans: CUDA events (external event nodes inside the graphs)
+    step = TrainStep(opt, graph, optim, flat, batches[0], dev, side_work=(clip_ctx.run if clip_ctx is not None else None),
+                     use_cuda_graph=not a.eager)
 
     def barrier():
         if world > 1:
@@ -223,29 +221,47 @@ def run_ours(a):
             tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
         return float(ms) / steps
 
-    def fresh(i):          # device-resident batch, grads reset (leaves are re-used across steps)
-        return resident[i % len(resident)]
+    def resident_step(i):     # batch already in HBM: device->device refresh of the step's input tensors, then the step
+        step.load(resident[i % len(resident)])
+        if clip_ctx is not None:
+            clip_ctx.static_images.copy_(clip_ctx.images[i % 2], non_blocking=True)
+        return step()
 
     for i in range(max(3, a.warmup)):
-        step(fresh(i))
-    # ---- device-resident throughput (value) with per-kernel timers
+        resident_step(i)
+    # ---- device-resident throughput (value)
     rn.TIMERS.reset()
-    rn.TIMERS.enabled = True
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    ms_step = timed(lambda i: step(fresh(i)), a.steps)
+    ms_step = timed(resident_step, a.steps)
     clocks = sampler.stop() if sampler else None
-    kernel_ms = rn.TIMERS.totals_ms()
     launches = rn.TIMERS.launches / a.steps
+    # per-kernel durations: eager = every launch of the timed region; graphs = the event nodes inside the graph, read after
+    # the last timed replay and after 5 more replays (a synchronize between them)
+    if a.eager:
+        kernel_ms = rn.TIMERS.totals_ms()
+        span_steps = a.steps
+    else:
+        acc, span_steps = {}, 0
+        for rep in range(6):
+            if rep:
+                resident_step(rep)
+            for k, (ms, n) in rn.TIMERS.graph_ms().items():
+                t = acc.setdefault(k, [0.0, 0])
+                t[0] += ms
+                t[1] += n
+            span_steps += 1
+        kernel_ms = {k: tuple(v) for k, v in acc.items()}
     rn.TIMERS.enabled = False
 
     # ---- end to end through the public API: pinned host batch -> device, step, loss back to the host
     def e2e_step(i):
-        var, _ = synthetic.to_device(batches[i % len(batches)], dev)
-        imgs = clip_ctx.h2d(i) if clip_ctx is not None else None
-        loss = step(var, imgs)
-        return float(loss)                         # device -> host read of the result
+        step.load(batches[i % len(batches)])
+        if clip_ctx is not None:
+            clip_ctx.static_images.copy_(clip_ctx.host_images[i % 2], non_blocking=True)
+        loss = step()
+        return float(loss["all"].detach())         # device -> host read of the result
     for i in range(3):
         e2e_step(i)
     ms_e2e = timed(e2e_step, a.steps)
@@ -262,14 +278,19 @@ def run_ours(a):
     bwd_avg = bwd_ms / max(bwd_n, 1)
     ffma_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
     achieved = pts * FLOP_BWD_PER_POINT / (bwd_avg * 1e-3) / 1e12 if bwd_avg > 0 else 0.0
-    roofline = dict(kernel="render_bwd_kernel<0>", bound="tensor", achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s",
-                    frac=achieved / pk["bf16_sustained"], traffic=None, peak_source=pk["source"] + " bf16 sustained (kernel timed inside the step)",
+    share = lambda ms: ms / span_steps / ms_step
+    roofline = dict(kernel="render_tc_bwd_kernel<0>", bound="tensor", achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s",
+                    frac=achieved / pk["bf16_sustained"], traffic=RENDER_BWD_DRAM_BYTES,
+                    peak_source=pk["source"] + " bf16 sustained (kernel timed inside the step)",
                     algorithmic_flops_per_launch=pts * FLOP_BWD_PER_POINT, avg_launch_ms=bwd_avg,
-                    note="FP32 FFMA parity path (1e-4 target rules out bf16/tf32 operands, BASELINE.md §2): the honest "
-                         "ceiling is the FP32 pipe",
+                    note="fp32-class products on tcgen05: every operand is a hi/lo bf16 pair and every product 3 MMAs (the 1e-4 "
+                         "parity target rules out plain bf16/tf32 operands, BASELINE.md §2), so this scheme tops out at 1/3 of "
+                         "the bf16 peak; flops follow SURVEY.md §8d's convention (2*MAC of the GEMMs as the reference runs them)",
+                    timing="CUDA events around the kernel on its launch stream" + ("" if a.eager else
+                           " (external event nodes inside the step's CUDA graph; 6 replays)"),
                     fp32_ffma_peak_tflops=ffma_peak, frac_of_fp32_ffma=achieved / ffma_peak,
-                    share_of_step=dict(render_bwd=bwd_ms / a.steps / ms_step, render_fwd=fwd_ms / a.steps / ms_step,
-                                       **{k: v[0] / a.steps / ms_step for k, v in kernel_ms.items() if k.startswith("sdf") or k.startswith("clip")}),
+                    share_of_step=dict(render_bwd=share(bwd_ms), render_fwd=share(fwd_ms),
+                                       **{k: share(v[0]) for k, v in kernel_ms.items() if k.startswith("sdf") or k.startswith("clip")}),
                     render_fwd_tflops=(pts * FLOP_FWD_PER_POINT / (fwd_ms / max(fwd_n, 1) * 1e-3) / 1e12) if fwd_ms > 0 else None)
     line = dict(metric=METRIC, value=images / (ms_step * 1e-3), unit=UNIT, n_gpus=world, steps=a.steps, warmup=max(3, a.warmup),
                 ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
@@ -277,6 +298,7 @@ def run_ours(a):
                 e2e=dict(value=images / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e, h2d_bytes_per_step=h2d_bytes,
                          d2h_bytes_per_step=4),
                 gpu_launches=launches, clocks=clocks, roofline=roofline)
+    line["config"]["execution"] = "eager launches" if a.eager else "CUDA graphs (forward+losses+backward, optimiser) replayed per step"
     if world == 1 and not a.no_cpu_baseline:
         rate, dt, cores = cpu_reference_rate(options.default_options(device="cpu"), 1, 1, 1)
         line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="port",

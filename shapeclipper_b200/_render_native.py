@@ -172,7 +172,9 @@ class KernelTimers:
 
     def __init__(self):
         self.enabled = False
+        self.capturing = False      # inside a CUDA-graph capture (step.TrainStep): spans become external event nodes
         self.events = {}
+        self.graph_events = {}
         self.launches = 0
 
     def reset(self):
@@ -189,6 +191,11 @@ class KernelTimers:
         torch.cuda.synchronize()
         return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.events.items()}
 
+    def graph_ms(self):
+        """Spans recorded while a CUDA graph was captured, as timed by the LAST replay: {name: (total ms, launches)}."""
+        torch.cuda.synchronize()
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.graph_events.items()}
+
 
 class _Span:
     def __init__(self, timers, name, device):
@@ -196,15 +203,16 @@ class _Span:
 
     def __enter__(self):
         if self.t.enabled:
-            self.a = torch.cuda.Event(enable_timing=True)
-            self.b = torch.cuda.Event(enable_timing=True)
+            ext = self.t.capturing
+            self.a = torch.cuda.Event(enable_timing=True, external=ext)
+            self.b = torch.cuda.Event(enable_timing=True, external=ext)
             self.a.record(torch.cuda.current_stream(self.device))
         return self
 
     def __exit__(self, *exc):
         if self.t.enabled:
             self.b.record(torch.cuda.current_stream(self.device))
-            self.t.events.setdefault(self.name, []).append((self.a, self.b))
+            (self.t.graph_events if self.t.capturing else self.t.events).setdefault(self.name, []).append((self.a, self.b))
         return False
 
 

@@ -270,6 +270,7 @@ class _BenchContext:
         g = torch.Generator().manual_seed(7)
         self.host_images = [torch.randn(batch, 3, 224, 224, generator=g).pin_memory() for _ in range(2)]
         self.images = [t.to(device) for t in self.host_images]
+        self.static_images = self.images[0].clone()      # the tensor a captured step reads; refreshed by copy_()
         bank = torch.nn.functional.normalize(torch.randn(bank_size, 512, generator=g), dim=-1).to(device)
         self.bank_hi, self.bank_lo = split_bf16(bank)
         self.sim = torch.empty(batch, bank_size, device=device)
@@ -284,8 +285,7 @@ class _BenchContext:
     def run(self, images=None):
         from . import _render_native as rn
         L = _lib.lib()
-        img = images if images is not None else self.images[self.i % 2]
-        self.i += 1
+        img = images if images is not None else self.static_images
         raw, emb, hi, lo = self.model.encode(img, want_planes=True)
         with torch.cuda.device(self.device):
             _lib.check(L.sc_cosine_topk(_p(hi), _p(lo), _p(self.bank_hi), _p(self.bank_lo), img.shape[0], self.bank_hi.shape[0],

@@ -243,7 +243,7 @@ extern "C" int sc_clip_encode(const ScClipConfig* cfg, const ScClipWeights* wts,
             w.x, (size_t)W, M, W, L.ln1_w, L.ln1_b, w.ln_hi, lo(w.ln_lo), nullptr, nullptr, nullptr, nullptr, T);
         SC_TRY(sc_gemm_bf16_tc(w.ln_hi, lo(w.ln_lo), L.qkv_w_hi, wlo(L.qkv_w_lo), M, 3 * W, W, L.qkv_b, nullptr, 0, 1.f,
                                w.qkv, nullptr, nullptr, stream));
-        const int att_threads = 128;
+        const int att_threads = 512;      // 16 warps share one (image, head)'s K/V tile: ~3 query rows per warp at T = 50
         const size_t att_smem = ((size_t)2 * T * 65 + (size_t)(att_threads / 32) * (T + 64)) * sizeof(float);
         if (att_smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem);

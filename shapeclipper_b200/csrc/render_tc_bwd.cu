@@ -35,20 +35,39 @@ constexpr int VA_V3 = 0, VA_W5 = 192, VA_B3 = 256, VA_B4 = 320, VA_B5F = 384, VA
               VA_B5 = 580, VA_BETA = 584, VA_FLOATS = 588;
 static_assert(G_W5 - G_V3 == VA_W5 - VA_V3 && G_BETA - G_V3 == VA_BETA - VA_V3, "vector accumulators mirror the G_* layout");
 
-// column sums over the 128 rows of the tile, added to a 64-entry shared accumulator (16 columns per thread)
-__device__ __forceinline__ void colsum_shared(float* acc64, const float (&v)[NC], int ch, int lane) {
+// column sums over the 128 rows of the tile, added to a 64-entry accumulator (16 columns per thread).
+// Butterfly transpose-reduce: after the exchange with lane ^ 16 a lane keeps 8 of its 16 columns, then 4, 2, 1 - 16
+// shuffles per warp instead of 80, and ONE atomic instruction (16 lanes, 16 addresses) instead of 16.
+__device__ __forceinline__ float colsum16(const float (&v)[NC], int lane) {
+    float a[8], b[4], c[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
 #pragma unroll
-    for (int i = 0; i < NC; ++i) {
-        const float s = warp_sum(v[i]);
-        if (lane == 0) atomicAdd(acc64 + NC * ch + i, s);
+    for (int i = 0; i < 8; ++i) {
+        const float send = h16 ? v[i] : v[i + 8], keep = h16 ? v[i + 8] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h8 ? a[i] : a[i + 4], keep = h8 ? a[i + 4] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h4 ? b[i] : b[i + 2], keep = h4 ? b[i + 2] : b[i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const float send = h2 ? c[0] : c[1], keep = h2 ? c[1] : c[0];
+    float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;                      // column (lane >> 1) & 15 of this thread's group, summed over the warp's 32 rows
+}
+__device__ __forceinline__ void colsum_shared(float* acc64, const float (&v)[NC], int ch, int lane) {
+    const float s = colsum16(v, lane);
+    if ((lane & 1) == 0) atomicAdd(acc64 + NC * ch + (lane >> 1), s);
 }
 __device__ __forceinline__ void colsum_global(float* acc64, const float (&v)[NC], int ch, int lane) {
-#pragma unroll
-    for (int i = 0; i < NC; ++i) {
-        const float s = warp_sum(v[i]);
-        if (lane == 0) atomicAdd(acc64 + NC * ch + i, s);
-    }
+    const float s = colsum16(v, lane);
+    if ((lane & 1) == 0) atomicAdd(acc64 + NC * ch + (lane >> 1), s);
 }
 // stash plane -> operand buffer (same thread mapping)
 __device__ __forceinline__ void plane_to_act(const TileTC& T, const float* plane, uint8_t* dst, float (&v)[NC]) {
@@ -198,16 +217,18 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 colsum_shared(vacc + VA_C2R, v, ch, lane);
                 plane_to_act(T, st + (TS_R + 1) * kStashPlane, T.Z(), h);      // r1 -> Z (h keeps this thread's r1 values)
                 T.gemm(TM_ACC0, T.Y(), false);                                   // V2T : r1_bar = V2^T o2_bar
+                T.commit();                                                      // the epilogue overlaps the weight-gradient MMAs
                 if (tid == 0) wgrad(WG_V2, T.Y(), T.Z());
-                T.finish_and_load(TM_ACC0, v);
+                T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) v[i] = h[i] > 0.f ? v[i] : 0.f;
                 row_store(T.X(), r, ch, v);                                      // o1_bar -> X
                 colsum_shared(vacc + VA_C1R, v, ch, lane);
                 plane_to_act(T, st + (TS_R + 0) * kStashPlane, T.U(), h);      // r0 -> U
                 T.gemm(TM_ACC0, T.X(), false);                                   // V1T
+                T.commit();
                 if (tid == 0) wgrad(WG_V1, T.X(), T.U());
-                T.finish_and_load(TM_ACC0, v);
+                T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) v[i] = h[i] > 0.f ? v[i] : 0.f;
                 row_store(T.Z(), r, ch, v);                                      // o0_bar -> Z  (Z: wgrad V2 completed with the V1T phase)
@@ -215,8 +236,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 plane_to_act(T, st + TS_FEAT * kStashPlane, T.Y(), h);         // feat -> Y
                 T.gemm(TM_ACC0, T.Z(), false);                                   // V0FT -> feat_bar
                 T.gemm(TM_ACC1, T.Z(), false);                                   // V0PT -> pe_bar (rgb)
+                T.commit();
                 if (tid == 0) { wgrad(WG_V0F, T.Z(), T.Y()); wgrad(WG_V0P, T.Z(), T.P()); }
-                T.finish_and_load(TM_ACC0, v);
+                T.wait_and_load(TM_ACC0, v);
                 st_store(st + TS_FB * kStashPlane, r, ch, v);
                 colsum_shared(vacc + VA_B5F, v, ch, lane);
                 tmem_ld_32x16(T.tmem + TM_ACC1 + ((uint32_t)(32 * (T.warp & 3)) << 16) + (uint32_t)c0, v);
@@ -343,12 +365,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 plane_to_act(T, st + (TS_H + l) * kStashPlane, hbuf, h);        // h_l (h keeps this thread's values)
                 if (l < 2) { T.gemm(TM_ACC1, acur, false); }                     // A2T | A1T  -> pe_bar
                 T.gemm(TM_ACC0, acur, false);                                    // W4T | W3T | B2T | B1T
+                T.commit();
                 if (tid == 0) {
                     wgrad(l == 3 ? WG_W4 : (l == 2 ? WG_W3 : (l == 1 ? WG_B2 : WG_B1)), acur, hbuf);
                     if (l < 2) wgrad(l == 1 ? WG_A2 : WG_A1, acur, T.P());
                 }
                 if (second) st_load(st + (TS_SB + l) * kStashPlane, r, ch, w2);
-                T.finish_and_load(TM_ACC0, v);
+                T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) {
                     float s, t;

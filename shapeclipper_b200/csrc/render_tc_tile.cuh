@@ -30,9 +30,12 @@ struct TileTC {
     __device__ __forceinline__ uint8_t* Z() const { return act[3]; }
     __device__ __forceinline__ uint8_t* U() const { return act[4]; }
 
-    // thread 0: commit the phase; everyone: wait for the accumulator, then read this thread's NC columns
-    __device__ __forceinline__ void finish_and_load(uint32_t acc_col, float (&v)[NC]) {
-        if (tid == 0) sctc::umma_commit(mma_done);
+    // thread 0: commit the phase's layer GEMMs. MMAs issued AFTER this (weight gradients) are covered by the NEXT phase's
+    // commit: their operand buffers must stay untouched until the next wait_and_load() has returned.
+    __device__ __forceinline__ void commit() { if (tid == 0) sctc::umma_commit(mma_done); }
+    __device__ __forceinline__ void finish_and_load(uint32_t acc_col, float (&v)[NC]) { commit(); wait_and_load(acc_col, v); }
+    // everyone: wait for the accumulator, then read this thread's NC columns
+    __device__ __forceinline__ void wait_and_load(uint32_t acc_col, float (&v)[NC]) {
         mark();
         scr::mbar_wait(mma_done, mma_phase);
         mark();

@@ -52,7 +52,9 @@ class HotPathGraph(nn.Module):
         iou = (nn_ * q).sum(1) / (nn_ + q - nn_ * q + 1.e-8).sum(1)
         probs = F.normalize((1 - iou) ** opt.reg.sample_temp, dim=-1, p=1)
         if getattr(opt.reg, "device_sampling", False):
-            return torch.multinomial(probs, V, replacement=False)
+            # V draws without replacement with probabilities `probs`: the V largest of probs / Exp(1) (the exponential-race
+            # form torch.multinomial itself uses), without multinomial's validity asserts -> capturable, 3 kernels.
+            return (probs / torch.empty_like(probs).exponential_(1.0)).topk(V, dim=-1).indices
         rows = []
         for p in probs.cpu().numpy():
             p = p / np.sum(p)

@@ -58,6 +58,13 @@ class Renderer(nn.Module):
             raise NotImplementedError("only render.normal_model == 'volume' (the reference default) is implemented")
         self.ray_sampler = UniformSampler(opt)
         self.N_samples = opt.render.n_samples_uniform
+        self._t_cache = {}
+
+    def _t_vals(self, S, dev):
+        key = (S, str(dev))
+        if self._t_cache.get("key") != key:
+            self._t_cache = {"key": key, "t": torch.linspace(0., 1., steps=S).to(dev)}
+        return self._t_cache["t"]
 
     def forward(self, opt, pose, intr, scale_dist, proj_latent_sdf, proj_latent_rgb, ray_idx=None, training=True,
                 visualize=False):
@@ -70,10 +77,13 @@ class Renderer(nn.Module):
         cam_loc, ray_dirs, depth_fac = camera.pixel_rays(pose, intr, opt.H, opt.W, ray_idx)
         B, R = ray_dirs.shape[0], ray_dirs.shape[1]
 
-        # CPU-generator draws, reference order (renderer.py:29,33,158)
-        u = torch.rand(B * R, S).to(dev) if training else None
-        eik_idx = torch.randint(S, (B * R,)).to(dev)
-        t_vals = torch.linspace(0., 1., steps=S).to(dev)
+        # CPU-generator draws, reference order (renderer.py:29,33,158). `opt.render.device_rng` draws the same
+        # distributions from the CUDA generator instead: no host work / pageable copy in the step, and the step becomes
+        # capturable in a CUDA graph (throughput mode; seeds then no longer reproduce the reference's samples).
+        rng_dev = dev if getattr(opt.render, "device_rng", False) else "cpu"
+        u = torch.rand(B * R, S, device=rng_dev).to(dev) if training else None
+        eik_idx = torch.randint(S, (B * R,), device=rng_dev).to(dev)
+        t_vals = self._t_vals(S, dev)
 
         cfg = dict(n_samples=S, beta_min=float(self.density.beta_min), cam_dist=float(opt.camera.dist), half_range=0.7,
                    bg_color=float(self.bg_color), normal_pow=float(opt.reg.normal_pow))
@@ -83,7 +93,7 @@ class Renderer(nn.Module):
 
         grad_eikonal = None
         if training:
-            uni = torch.empty(B * R, 3).uniform_(self.eik_range[0], self.eik_range[1]).to(dev).reshape(B, R, 3)
+            uni = torch.empty(B * R, 3, device=rng_dev).uniform_(self.eik_range[0], self.eik_range[1]).to(dev).reshape(B, R, 3)
             sd_ray = scale_dist.unsqueeze(-1).expand(B, R).reshape(-1)
             u_at = u.gather(1, eik_idx.unsqueeze(-1)).squeeze(-1)
             z_eik = UniformSampler.depth_at(opt, sd_ray, t_vals, eik_idx, u_at).reshape(B, R, 1)

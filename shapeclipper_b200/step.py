@@ -1,0 +1,106 @@
+"""One training iteration of the hot path, shaped like Runner.train_iteration (model/runner.py:235-292):
+
+    optim.zero_grad() -> graph.forward(opt, var, training=True, get_loss=True) -> loss.all.backward()
+    -> [flat gradient all-reduce, N > 1] -> optim.step()
+
+The reference runs this as ~2 000 eager kernel launches with ~20 host syncs. Here the step is launch-bound once the
+renders are fused (two render kernels each way + ~350 small torch kernels for rays, losses and Adam), so `TrainStep`
+captures it ONCE into CUDA graphs (forward + losses + backward in one, the optimiser in another; the NCCL all-reduce
+between them stays eager) and replays them: same kernels, same arithmetic, no per-launch host cost.
+
+Requirements for capture (checked): `opt.render.device_rng` and `opt.reg.device_sampling` (every random draw on the
+CUDA generator, no host round trip) and a capturable optimiser (`torch.optim.Adam(..., capturable=True)`).
+Without them the step runs eagerly with identical results to calling the pieces by hand.
+"""
+import torch
+
+from . import _render_native as rn
+from .options import Options
+
+GRAD_LEAVES = ("pose", "intr", "scale_dist", "proj_latent_sdf", "proj_latent_rgb",
+               "pose_NN", "intr_NN", "scale_dist_NN", "proj_latent_rgb_NN")
+
+
+class TrainStep:
+    def __init__(self, opt, graph, optim, flat_grads, example_batch, device, side_work=None, use_cuda_graph=True,
+                 warmup=3):
+        """graph: HotPathGraph; flat_grads: dist.FlatGradients over the optimiser's parameters; example_batch: a host
+        batch (synthetic.make_batch layout) fixing every shape; side_work: optional callable run at the start of each
+        step on the same stream (bench.py: the CLIP encode + k-NN leg)."""
+        self.opt, self.graph, self.optim, self.flat = opt, graph, optim, flat_grads
+        self.device = torch.device(device)
+        self.side_work = side_work
+        self.var = Options()
+        for k, t in example_batch.items():
+            d = t.to(self.device)
+            if k in GRAD_LEAVES:
+                d.requires_grad_(True)
+            self.var[k] = d
+        self.loss = None
+        self.launches_per_step = None
+        self._g_main = self._g_optim = None
+        self.use_cuda_graph = bool(use_cuda_graph)
+        if self.use_cuda_graph:
+            if not (getattr(opt.render, "device_rng", False) and getattr(opt.reg, "device_sampling", False)):
+                raise ValueError("CUDA-graph capture needs opt.render.device_rng and opt.reg.device_sampling")
+            if not all(g.get("capturable", False) for g in optim.param_groups):
+                raise ValueError("CUDA-graph capture needs a capturable optimiser (Adam(..., capturable=True))")
+            self._capture(warmup)
+
+    # ------------------------------------------------------------------------------------------------------
+    def load(self, batch):
+        """Host (pinned) batch -> the step's static device tensors; async on the current stream."""
+        with torch.no_grad():
+            for k, t in batch.items():
+                self.var[k].copy_(t, non_blocking=True)
+
+    def _forward_backward(self):
+        self.flat.zero()
+        for k in GRAD_LEAVES:
+            if k in self.var:
+                self.var[k].grad = None
+        if self.side_work is not None:
+            self.side_work()
+        _, loss = self.graph(self.opt, self.var, training=True, get_loss=True)
+        loss["all"].backward()
+        return loss
+
+    def _capture(self, warmup):
+        timers_were = rn.TIMERS.enabled
+        rn.TIMERS.enabled = False
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(max(1, warmup)):              # allocator / lazy-init warm-up on the capture stream
+                self._forward_backward()
+                self.flat.all_reduce()
+                self.optim.step()
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        rn.TIMERS.enabled = timers_were
+        rn.TIMERS.capturing = True
+        n0 = rn.TIMERS.launches
+        self._g_main = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_main):
+            self.loss = self._forward_backward()
+        self._g_optim = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_optim, pool=self._g_main.pool()):
+            self.optim.step()
+        rn.TIMERS.capturing = False
+        self.launches_per_step = rn.TIMERS.launches - n0
+        rn.TIMERS.launches = n0
+        rn.invalidate_blob_cache()        # blobs cached during capture live in the graph's pool and go stale on replay
+
+    # ------------------------------------------------------------------------------------------------------
+    def __call__(self):
+        """Run one step on the tensors in self.var; returns the loss dict (device scalars; 'all' is the total)."""
+        if self._g_main is None:
+            self.loss = self._forward_backward()
+            self.flat.all_reduce()
+            self.optim.step()
+            return self.loss
+        self._g_main.replay()
+        self.flat.all_reduce()
+        self._g_optim.replay()
+        rn.TIMERS.count(self.launches_per_step)
+        return self.loss
