@@ -168,8 +168,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {     //
     return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+#ifdef SC_TC_NOINLINE_ISSUE          // the backward kernel (the forward kernel's loops keep its issue code cache-resident: inline is faster there)
+#define SC_TC_ISSUE_FN static __device__ __noinline__
+#else
+#define SC_TC_ISSUE_FN __device__ __forceinline__
+#endif
 // D[128 x 64] (+)= ACT[128 x 64] . W^T   (3 MMAs per 16-wide k-step). Issued by ONE thread.
-__device__ __forceinline__ void issue_layer_gemm(uint32_t tmem_d, const uint8_t* act, const uint8_t* w, bool accumulate) {
+// NOT inlined in the backward kernel (here and issue_wgrad): it has ~60 issue sites of 12-24 MMAs each; inlined they were 5 k
+// SASS instructions (25 % of the kernel) that the issuing warp walked once per tile, every line an instruction-cache miss
+// on the critical path of the phase (ncu: 29 % of the warp samples stalled on instruction fetch).
+SC_TC_ISSUE_FN void issue_layer_gemm(uint32_t tmem_d, const uint8_t* act, const uint8_t* w, bool accumulate) {
     constexpr uint32_t idesc = sctc::make_idesc_bf16(128, 64);
     const uint64_t ah = sctc::make_smem_desc_k128(act), al = sctc::make_smem_desc_k128(act + kPlaneBytes);
     const uint64_t wh = sctc::make_smem_desc_k128(w), wl = sctc::make_smem_desc_k128(w + kWPlaneBytes);
@@ -182,7 +190,7 @@ __device__ __forceinline__ void issue_layer_gemm(uint32_t tmem_d, const uint8_t*
     }
 }
 // D[64 x 64] += L^T . R over the tile's 128 points (L, R = plane pairs). Issued by ONE thread.
-__device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, const uint8_t* L, const uint8_t* R, bool accumulate) {
+SC_TC_ISSUE_FN void issue_wgrad(uint32_t tmem_d, const uint8_t* L, const uint8_t* R, bool accumulate) {
     constexpr uint32_t idesc = make_idesc_bf16_mn(64, 64);
     const uint64_t lh = make_smem_desc_mn128(L), ll = make_smem_desc_mn128(L + kPlaneBytes);
     const uint64_t rh = make_smem_desc_mn128(R), rl = make_smem_desc_mn128(R + kPlaneBytes);

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define SC_TC_NOINLINE_ISSUE 1
 #include "render_ray.cuh"
 #include "render_tc_tile.cuh"
 
