@@ -69,11 +69,20 @@ def encode_image(p, cfg, images):
     return x @ p["proj"]
 
 
-def calc_matches(features, k_nearest=6):
-    """NN_annotator.calc_matches with opt.thres = None (CLIP_anno.py:29-41): per query cosine to all + top-k."""
+def calc_matches(features, k_nearest=6, thres=None):
+    """NN_annotator.calc_matches (CLIP_anno.py:29-57): per query cosine to all + top-k; with `thres` (opt.thres) the
+    query followed by k-1 random picks among the similarities in [thres, 1) when there are enough of them."""
     idx, val = [], []
     for i in range(features.shape[0]):
         cos = (features[i:i + 1] * features).sum(dim=1)
+        if thres is not None:
+            index = ((cos >= thres) & (cos < 1.)).nonzero()
+            n_valid = len(index)
+            if n_valid >= k_nearest - 1:
+                sampled = index[torch.randperm(n_valid)[:k_nearest - 1]].squeeze(1)
+                both = torch.cat([torch.tensor([i]), sampled], dim=0)
+                idx.append(both); val.append(cos[both])
+                continue
         v, j = cos.topk(k_nearest, largest=True)
         idx.append(j); val.append(v)
     return torch.stack(idx), torch.stack(val)

@@ -234,9 +234,12 @@ def load(name="ViT-L/14", device="cuda", precision="split", state_dict=None):
 
 
 @torch.no_grad()
-def calc_matches(features, k_nearest=6, bank=None):
+def calc_matches(features, k_nearest=6, bank=None, thres=None):
     """Cosine k-NN of L2-normalised features [N,D] against themselves (or `bank`): (indices [N,k], values [N,k]).
-    NN_annotator.calc_matches with opt.thres = None; one tcgen05 GEMM + one top-k kernel instead of N GEMVs."""
+    NN_annotator.calc_matches (CLIP_anno.py:29-57): one tcgen05 GEMM + one top-k kernel instead of N GEMVs.
+    `thres` (opt.thres, CLIP_anno.py:42-54): rows with at least k-1 similarities in [thres, 1) return the query itself
+    followed by k-1 of those, drawn with torch.randperm from the CPU generator in row order exactly as the reference
+    does (equal seeds give equal draws); the other rows fall back to top-k."""
     L = _lib.lib()
     _lib.require_cuda(features)
     f = features.float().contiguous()
@@ -258,7 +261,30 @@ def calc_matches(features, k_nearest=6, bank=None):
                                     _p(idx), _lib.stream_of(f)), "sc_cosine_topk")
     from . import _render_native as rn
     rn.TIMERS.count(2)
-    return idx.long(), val
+    idx = idx.long()
+    if thres is None:
+        return idx, val
+    if bank is not None:
+        raise ValueError("thres sampling is defined for the self-similarity case of the reference (no separate bank)")
+    s = sim[:, :Nb]
+    ok = (s >= thres) & (s < 1.)
+    counts = ok.sum(1).cpu()                                   # the only host round trip: the draws happen on the CPU generator
+    cols = ok.nonzero()[:, 1]                                  # row-major, ascending column inside a row (= .nonzero() per row)
+    starts = torch.cumsum(counts, 0) - counts
+    rows_i, rows_sel = [], []
+    for i in range(N):
+        n_valid = int(counts[i])
+        if n_valid < k_nearest - 1:
+            continue
+        rows_i.append(i)
+        rows_sel.append(starts[i] + torch.randperm(n_valid)[:k_nearest - 1])
+    if rows_i:
+        ri = torch.tensor(rows_i, device=f.device)
+        sel = cols[torch.stack(rows_sel).to(f.device)]       # [n_rows, k-1]
+        full = torch.cat([ri.unsqueeze(1), sel], dim=1)
+        idx[ri] = full
+        val[ri] = torch.gather(s[ri], 1, full)
+    return idx, val
 
 
 class _BenchContext:

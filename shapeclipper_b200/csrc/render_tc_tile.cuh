@@ -19,7 +19,7 @@ struct TileTC {
     float beta;
 #ifdef SC_TC_TRACE
     long long* trace; int trace_n;
-    __device__ __forceinline__ void mark() { if (trace && blockIdx.x == 0 && (tid == 0 || tid == 300) && trace_n < 120) trace[(tid ? 128 : 0) + trace_n++] = clock64(); }
+    __device__ __forceinline__ void mark() { if (trace && blockIdx.x == 0 && (tid == 0 || tid == 300) && trace_n < 500) trace[(tid ? 512 : 0) + trace_n++] = clock64(); }
 #else
     __device__ __forceinline__ void mark() {}
 #endif

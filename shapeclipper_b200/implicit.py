@@ -139,6 +139,23 @@ class RGBNetwork(nn.Module):
         return [getattr(self, "lin%d" % l) for l in range(self.num_layers - 1)]
 
     def forward(self, points_raw, proj_latent, sdf_feature):
-        raise NotImplementedError(
-            "RGBNetwork is evaluated inside the fused render kernel (Renderer.forward); the reference never calls it "
-            "anywhere else (model/renderer.py:110)")
+        """points_raw [N,3], proj_latent [N,64], sdf_feature [N,64] -> rgb [N,3] (model/implicit.py:220-239).
+        NOT the hot path: inside Renderer.forward the RGB MLP is fused into the render kernel. This standalone form only
+        serves the 200-ray debug output of `visualize=True` (model/renderer.py:174-183) and direct callers; it is a few
+        torch ops on the caller's device."""
+        x = torch.cat([points_raw[:, :1].abs(), points_raw[:, 1:]], dim=-1) if self.force_symmetry else points_raw
+        h = torch.cat([positional_encoding(x, 6), proj_latent, sdf_feature], dim=-1)
+        lins = self.linears()
+        for l, lin in enumerate(lins):
+            h = lin(h)
+            if l < len(lins) - 1:
+                h = self.relu(h)
+        return self.sigmoid(h)
+
+
+def positional_encoding(x, n_freq):
+    """[x, sin(2^0 x), cos(2^0 x), ..., sin(2^(L-1) x), cos(2^(L-1) x)] (model/implicit.py:28-38), 3 -> 3 + 6 L."""
+    out = [x]
+    for f in range(n_freq):
+        out += [torch.sin(x * float(2 ** f)), torch.cos(x * float(2 ** f))]
+    return torch.cat(out, dim=-1)

@@ -70,8 +70,6 @@ class Renderer(nn.Module):
                 visualize=False):
         if opt.camera.model != "perspective":
             raise NotImplementedError("only the perspective camera of the reference config is implemented")
-        if visualize:
-            raise NotImplementedError("visualize=True (200 debug rays, model/renderer.py:174-183) is not implemented")
         dev = pose.device
         S = self.N_samples
         cam_loc, ray_dirs, depth_fac = camera.pixel_rays(pose, intr, opt.H, opt.W, ray_idx)
@@ -101,4 +99,34 @@ class Renderer(nn.Module):
             eik_pts = torch.cat([uni, near_pts], dim=1).reshape(-1, 3)
             _, _, g = self.sdf_network.get_conditional_output(opt, B, eik_pts, proj_latent_sdf, compute_grad=True)
             grad_eikonal = g.norm(2, dim=1)
+        if visualize:
+            return (rgb, mask, mask_hard, depth, normal, grad_eikonal) + self._visualize_rays(
+                opt, cam_loc, ray_dirs, scale_dist, t_vals, u, proj_latent_sdf, proj_latent_rgb)
         return rgb, mask, mask_hard, depth, normal, grad_eikonal
+
+    @torch.no_grad()
+    def _visualize_rays(self, opt, cam_loc, ray_dirs, scale_dist, t_vals, u, z_sdf, z_rgb, n_vis=200):
+        """Per-sample points / opacity / colour of 200 random rays (model/renderer.py:174-183, 212-215): debug output of
+        evaluate(visualize=True), not the hot path. SDF + features come from the point-query kernel; the per-sample
+        colours are the only place the standalone RGBNetwork.forward runs."""
+        B, R, S = ray_dirs.shape[0], ray_dirs.shape[1], self.N_samples
+        dev = ray_dirs.device
+        idx = torch.randperm(R)[:n_vis].to(dev)                       # CPU generator, drawn last as in the reference
+        n = idx.numel()
+        d = ray_dirs[:, idx]                                           # [B,n,3]
+        s_idx = torch.arange(S, device=dev).repeat(B * n)
+        sd = scale_dist.reshape(B, 1, 1).expand(B, n, S).reshape(-1)
+        u_sel = None
+        if u is not None:
+            u_sel = u.reshape(B, R, S)[:, idx].reshape(-1)
+        z = UniformSampler.depth_at(opt, sd, t_vals, s_idx, u_sel).reshape(B, n, S)
+        pts = cam_loc.reshape(B, 1, 1, 3) + z.unsqueeze(-1) * d.unsqueeze(2)        # [B,n,S,3]
+        flat = pts.reshape(-1, 3).contiguous()
+        sdf, feat, _ = self.sdf_network.get_conditional_output(opt, B, flat, z_sdf, compute_grad=False)
+        sigma = self.density(sdf).reshape(B, n, S)
+        delta = torch.cat([z[..., 1:] - z[..., :-1], torch.zeros_like(z[..., :1])], dim=-1)
+        opacity = (1 - torch.exp(-delta * sigma)).reshape(B, n * S, 1)
+        lat = z_rgb.reshape(B, 1, -1).expand(B, n * S, z_rgb.shape[-1]).reshape(B * n * S, -1)
+        rgb = self.rgb_network(flat, lat, feat).reshape(B, n * S, 3)
+        transparency = torch.cat([opacity, 1 - opacity, torch.zeros_like(opacity)], dim=-1)
+        return pts.reshape(B, n * S, 3), transparency, torch.cat([rgb, opacity], dim=-1)

@@ -105,6 +105,26 @@ def case_render(mods, name, H, W, B, n_rays, training, seed):
     print("wrote", name, {n: (tuple(o.shape) if o is not None else None) for n, o in fx["outputs"].items()})
 
 
+def case_visualize(mods, name, H, W, B, seed):
+    """Renderer.forward(..., training=False, visualize=True): the three extra debug tensors (model/renderer.py:174-183)."""
+    opt = rh.load_reference_opt(H=H, W=W)
+    sdf, rgb, ren = make_networks(mods, opt, seed)
+    pose, intr, sd = random_camera(mods, opt, B)
+    zs, zr = torch.randn(B, 64) * 0.3, torch.randn(B, 64) * 0.3
+    torch.manual_seed(seed + 100)
+    with torch.no_grad():
+        outs = ren(opt, pose, intr, sd, zs, zr, ray_idx=None, training=False, visualize=True)
+    names = ["rgb", "mask", "mask_hard", "depth", "normal", "grad_eik", "points_sampled", "transparency_sampled", "rgb_sampled"]
+    torch.save(dict(H=H, W=W, B=B, seed=seed + 100,
+                    sdf_params={k: v.detach().clone() for k, v in sdf.state_dict().items()},
+                    rgb_params={k: v.detach().clone() for k, v in rgb.state_dict().items()},
+                    beta=ren.density.beta.detach().clone(),
+                    inputs=dict(pose=pose, intr=intr, scale_dist=sd, z_sdf=zs, z_rgb=zr),
+                    outputs={n: (o.detach().clone() if o is not None else None) for n, o in zip(names, outs)}),
+               os.path.join(OUT, name + ".pt"))
+    print("wrote", name, [tuple(o.shape) for o in outs[6:]])
+
+
 def case_sdf_query(mods, name, seed):
     opt = rh.load_reference_opt()
     sdf, _, _ = make_networks(mods, opt, seed)
@@ -140,6 +160,10 @@ def case_losses(mods, name, seed):
 def main():
     os.makedirs(OUT, exist_ok=True)
     mods = rh.import_reference()
+    if "--only-visualize" in sys.argv:
+        case_visualize(mods, "render_visualize_10x10", 10, 10, 2, seed=6)
+        return
+    case_visualize(mods, "render_visualize_10x10", 10, 10, 2, seed=6)
     case_render(mods, "render_eval_12x12", 12, 12, 2, None, False, seed=1)
     case_render(mods, "render_train_40rays", 16, 16, 2, 40, True, seed=2)
     case_render(mods, "render_train_full_8x8", 8, 8, 1, None, True, seed=3)

@@ -82,3 +82,27 @@ def test_calc_matches_matches_oracle():
     assert torch.allclose(got_v.cpu(), want_v, atol=2e-5)
     assert (got_i.cpu() == want_i).float().mean() > 0.995       # identical except exact-tie / 1e-6 near-ties
     assert (got_i[:, 0].cpu() == torch.arange(300)).all()
+
+
+def test_calc_matches_threshold_sampling_matches_oracle():
+    """opt.thres branch (CLIP_anno.py:42-54): same CPU-generator draws as the reference's loop -> same neighbours.
+    Features are scaled to norm 0.999 so that the self-similarity (0.998) is robustly inside [thres, 1) for both
+    implementations (with unit norms the reference's `cos_sim < 1.` test on the query itself is decided by fp32 rounding)."""
+    from shapeclipper_b200 import clip
+    torch.manual_seed(5)
+    centres = torch.nn.functional.normalize(torch.randn(6, 512), dim=-1)
+    f = torch.nn.functional.normalize(centres.repeat_interleave(40, 0) + 0.035 * torch.randn(240, 512), dim=-1)
+    f[200:] = torch.nn.functional.normalize(torch.randn(40, 512), dim=-1)       # rows without enough neighbours -> top-k
+    f = f * 0.999
+    cos = f @ f.T
+    thres = 0.55
+    while float((cos - thres).abs().min()) < 1e-5:
+        thres += 1e-4
+    torch.manual_seed(9)
+    want_i, want_v = clip_ref.calc_matches(f, 6, thres=thres)
+    torch.manual_seed(9)
+    got_i, got_v = clip.calc_matches(f.cuda(), 6, thres=thres)
+    assert (want_i[:200, 0] == torch.arange(200)).all() and float(want_v[:200, 1:].min()) >= thres      # sampled rows
+    assert (got_i[:200].cpu() == want_i[:200]).all()
+    assert torch.allclose(got_v.cpu(), want_v, atol=2e-5)
+    assert (got_i[200:].cpu() == want_i[200:]).float().mean() > 0.97       # top-k rows: near-ties may swap

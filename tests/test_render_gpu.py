@@ -92,6 +92,21 @@ def test_eval_render_matches_reference_golden(golden_dir):
     _check_outputs(out, fx["outputs"], NAMES, fx.get("outputs64"))
 
 
+def test_visualize_branch_matches_reference_golden(golden_dir):
+    """visualize=True (model/renderer.py:174-183): per-sample points / opacity / colour of the randperm-selected rays."""
+    fx = _load(golden_dir, "render_visualize_10x10")
+    opt, sdf, rgb, ren = _build(fx, fx["H"], fx["W"])
+    i = {k: v.cuda() for k, v in fx["inputs"].items()}
+    torch.manual_seed(fx["seed"])
+    with torch.no_grad():
+        out = ren(opt, i["pose"], i["intr"], i["scale_dist"], i["z_sdf"], i["z_rgb"], ray_idx=None, training=False, visualize=True)
+    assert len(out) == 9
+    _check_outputs(out[:6], fx["outputs"], NAMES)
+    for k, nm in zip(out[6:], ("points_sampled", "transparency_sampled", "rgb_sampled")):
+        assert tuple(k.shape) == tuple(fx["outputs"][nm].shape)
+        _close(k, fx["outputs"][nm], nm)
+
+
 @pytest.mark.parametrize("name", ["render_train_40rays", "render_train_full_8x8"])
 def test_training_render_forward_matches_reference_golden(golden_dir, name):
     fx = _load(golden_dir, name)
