@@ -125,6 +125,12 @@ int sc_render_tc_pack_weights(const float* const* w, const float* const* b, cons
                               cudaStream_t stream);
 int sc_render_tc_forward(const ScRenderArgs* args, cudaStream_t stream);
 int sc_render_tc_backward(const ScRenderArgs* args, cudaStream_t stream);
+/* Second generation of the tensor-core kernels: two independent 64-point tile chains per CTA (csrc/render_tc2.cuh). Same
+ * ScRenderArgs, blob (sc_render_tc_pack_weights), scratch (sc_render_tc_scratch_bytes), partials and finalize as above.
+ * Rays must fit one 64-point tile: sc_render_tc2_supported(mode, n_samples) says whether (4 <= S <= 64, S | 64). */
+int sc_render_tc2_supported(int mode, int n_samples);
+int sc_render_tc2_forward(const ScRenderArgs* args, cudaStream_t stream);
+int sc_render_tc2_backward(const ScRenderArgs* args, cudaStream_t stream);
 int sc_render_grad_finalize(const float* grad_partial, int n_ctas, const float* cb_bar, const float* z_sdf,
                             const float* z_rgb, const float* blob, int batch, float* const* out_w,
                             float* const* out_b, float* z_sdf_bar, float* z_rgb_bar, float* beta_bar,

@@ -47,6 +47,12 @@ def declare(L):
     L.sc_render_tc_pack_weights.restype = i
     L.sc_render_tc_forward.argtypes = [ctypes.POINTER(ScRenderArgs), vp]
     L.sc_render_tc_forward.restype = i
+    L.sc_render_tc2_supported.argtypes = [i, i]
+    L.sc_render_tc2_supported.restype = i
+    L.sc_render_tc2_forward.argtypes = [ctypes.POINTER(ScRenderArgs), vp]
+    L.sc_render_tc2_forward.restype = i
+    L.sc_render_tc2_backward.argtypes = [ctypes.POINTER(ScRenderArgs), vp]
+    L.sc_render_tc2_backward.restype = i
     if hasattr(L, "sc_render_tc_backward"):
         L.sc_render_tc_backward.argtypes = [ctypes.POINTER(ScRenderArgs), vp]
         L.sc_render_tc_backward.restype = i
@@ -219,13 +225,25 @@ class _Span:
 TIMERS = KernelTimers()
 
 
+def _entry(L, direction, tc, args):
+    """tc: False = FP32 FFMA kernels, True / "tc" = tensor-core generation 1, "tc2" = generation 2 (two 64-point chains per
+    CTA; falls back to generation 1 for sample counts that do not fit a 64-point tile)."""
+    if not tc:
+        name = "sc_render_" + direction
+    elif tc == "tc2" and L.sc_render_tc2_supported(args.mode, args.n_samples):
+        name = "sc_render_tc2_" + direction
+    else:
+        name = "sc_render_tc_" + direction
+    return getattr(L, name), name
+
+
 def launch_forward(args, device, tc=False):
     L = _lib.lib()
     with torch.cuda.device(device):
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         with TIMERS.span("render_fwd" if args.mode == 0 else "sdf_query_fwd", device):
-            fn = L.sc_render_tc_forward if tc else L.sc_render_forward
-            _lib.check(fn(ctypes.byref(args), stream), "sc_render_tc_forward" if tc else "sc_render_forward")
+            fn, name = _entry(L, "forward", tc, args)
+            _lib.check(fn(ctypes.byref(args), stream), name)
     TIMERS.count()
 
 
@@ -234,6 +252,6 @@ def launch_backward(args, device, tc=False):
     with torch.cuda.device(device):
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
         with TIMERS.span("render_bwd" if args.mode == 0 else "sdf_query_bwd", device):
-            fn = L.sc_render_tc_backward if tc else L.sc_render_backward
-            _lib.check(fn(ctypes.byref(args), stream), "sc_render_tc_backward" if tc else "sc_render_backward")
+            fn, name = _entry(L, "backward", tc, args)
+            _lib.check(fn(ctypes.byref(args), stream), name)
     TIMERS.count()

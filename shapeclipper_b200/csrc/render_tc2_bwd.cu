@@ -1,0 +1,480 @@
+// render_tc2_bwd.cu — two-chain tensor-core BACKWARD render / SDF-query kernel (see render_tc2.cuh; algorithm and phase
+// order identical to render_tc_bwd.cu, executed by two independent 8-warp groups on 64-point tiles).
+//
+// Per tile: recompute the forward (stashing H, Q, FEAT, R, GPE in the group's L2-resident scratch), compositing adjoint,
+// RGB backward, second-order sweep, first-order sweep. Layer GEMMs: UMMA 64x64x16 bursts into the group's TMEM accumulators;
+// weight gradients: UMMA 64x64x16 over the tile's 64 points accumulating into the 12 TMEM-resident matrices shared by both
+// groups (zeroed at kernel start, flushed once at the end). Vector gradients accumulate in shared memory.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SC_TC_NOINLINE_ISSUE 1
+#include "render_ray2.cuh"
+
+namespace sct2 {
+
+using namespace scr;
+// segment / weight-gradient ids of generation 1 (sct) take precedence over the FFMA blob's ids of the same name (scr)
+using sct::A0N; using sct::B1N; using sct::A1N; using sct::B2N; using sct::A2N; using sct::W3N; using sct::W4N; using sct::W5FN; using sct::V0PN; using sct::V0FN; using sct::V1N; using sct::V2N; using sct::W4T; using sct::W3T; using sct::B2T; using sct::B1T; using sct::A2T; using sct::A1T; using sct::A0T; using sct::W5FT; using sct::V2T; using sct::V1T; using sct::V0FT; using sct::V0PT;
+using sct::WG_A0; using sct::WG_A1; using sct::WG_A2; using sct::WG_B1; using sct::WG_B2; using sct::WG_W3; using sct::WG_W4; using sct::WG_W5F; using sct::WG_V0P; using sct::WG_V0F; using sct::WG_V1; using sct::WG_V2;
+using sct::wg_taddr;
+
+__device__ __forceinline__ void build_seq_bwd(int8_t* seq, int& len, int mode, bool second)
+{
+    int n = 0;
+    const int8_t base[] = {A0N, B1N, A1N, B2N, A2N, W3N, W4N};
+    for (int i = 0; i < 7; ++i) seq[n++] = base[i];
+    if (mode == 0) { seq[n++] = W5FN; seq[n++] = V0PN; seq[n++] = V0FN; seq[n++] = V1N; seq[n++] = V2N; }
+    if (second) { const int8_t g[] = {W4T, W3T, B2T, B1T, A2T, A1T, A0T}; for (int i = 0; i < 7; ++i) seq[n++] = g[i]; }
+    if (mode == 0) { seq[n++] = V2T; seq[n++] = V1T; seq[n++] = V0FT; seq[n++] = V0PT; }
+    if (second) { const int8_t s2[] = {A0N, A1N, B1N, A2N, B2N, W3N, W4N}; for (int i = 0; i < 7; ++i) seq[n++] = s2[i]; }
+    if (mode == 0) seq[n++] = W5FT;
+    const int8_t f1[] = {W4T, W3T, A2T, B2T, A1T, B1T, A0T};
+    for (int i = 0; i < 7; ++i) seq[n++] = f1[i];
+    len = n;
+}
+
+// shared-memory vector-gradient accumulators (floats), same relative order as the G_* tail of the folded gradient layout
+constexpr int VA_V3 = 0, VA_W5 = 192, VA_B3 = 256, VA_B4 = 320, VA_B5F = 384, VA_C1R = 448, VA_C2R = 512, VA_C3R = 576,
+              VA_B5 = 580, VA_BETA = 584, VA_FLOATS = 588;
+static_assert(G_W5 - G_V3 == VA_W5 - VA_V3 && G_BETA - G_V3 == VA_BETA - VA_V3, "vector accumulators mirror the G_* layout");
+
+// column sums over the 64 rows of the tile, added to a 64-entry accumulator. A warp holds 16 rows x 2 column groups (lanes
+// 0-15 / 16-31): butterfly transpose-reduce inside each 16-lane half — after the exchange with lane ^ 8 a lane keeps 8 of
+// its 16 columns, then 4, 2, 1 (15 shuffles) — then ONE atomic instruction, 32 lanes on 32 distinct columns.
+__device__ __forceinline__ float colsum16(const float (&v)[NC], int lane) {
+    float a[8], b[4], c[2];
+    const bool h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = h8 ? v[i] : v[i + 8], keep = h8 ? v[i + 8] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h4 ? a[i] : a[i + 4], keep = h4 ? a[i + 4] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h2 ? b[i] : b[i + 2], keep = h2 ? b[i + 2] : b[i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const float send = h1 ? c[0] : c[1], keep = h1 ? c[1] : c[0];
+    return keep + __shfl_xor_sync(0xffffffffu, send, 1);      // column (lane & 15) of this thread's group, summed over 16 rows
+}
+__device__ __forceinline__ void colsum_shared(float* acc64, const float (&v)[NC], int ch, int lane) {
+    atomicAdd(acc64 + NC * ch + (lane & 15), colsum16(v, lane));
+}
+__device__ __forceinline__ void colsum_global(float* acc64, const float (&v)[NC], int ch, int lane) {
+    atomicAdd(acc64 + NC * ch + (lane & 15), colsum16(v, lane));
+}
+// stash plane -> operand buffer (same thread mapping)
+__device__ __forceinline__ void plane_to_act(const TileTC2& T, const float* plane, uint8_t* dst, float (&v)[NC]) {
+    st_load(plane, T.row, T.ch, v);
+    row_store(dst, T.row, T.ch, v);
+}
+// pe_bar (this thread's 16 columns of row r) folded into x~_bar: XTB[k % 3][r] += pe_bar_k * d pe_k / d x~
+__device__ __forceinline__ void fold_pe_tc(const TileTC2& T, const float (&v)[NC]) {
+    float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int k = NC * T.ch + i;
+        if (k < NPE) g[k % 3] = fmaf(v[i], dpe_tc(T.P(), k, T.row), g[k % 3]);
+    }
+    if (NC * T.ch < NPE) {
+        atomicAdd(T.pv(PV_XTB0) + T.row, g[0]); atomicAdd(T.pv(PV_XTB1) + T.row, g[1]); atomicAdd(T.pv(PV_XTB2) + T.row, g[2]);
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) render_tc2_bwd_kernel(const ScRenderArgs a, float* stash_base)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    int8_t* seq = reinterpret_cast<int8_t*>(reinterpret_cast<float*>(smem + SMB_F32) + SF_MISC);
+    int& seq_len = *reinterpret_cast<int*>(reinterpret_cast<float*>(smem + SMB_F32) + SF_MISC + 16);
+    float* vacc = reinterpret_cast<float*>(smem + SMB_F32) + SF_VACC;
+    const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.blob);
+
+    const bool second = (MODE == 0) || (a.want_grad && a.grad_bar != nullptr);
+    float* part = a.grad_partial + (size_t)blockIdx.x * kGradFloats;
+    for (int i = threadIdx.x; i < kGradFloats; i += kThreads) part[i] = 0.f;
+    for (int i = threadIdx.x; i < VA_FLOATS; i += kThreads) vacc[i] = 0.f;
+    if (threadIdx.x == 0) { int len; build_seq_bwd(seq, len, MODE, second); seq_len = len; }
+    const uint32_t tmem = tc2_prologue(smem, blob);
+    {   // zero the 12 weight-gradient accumulators (TMEM columns 128..511): warp w clears its sub-partition's 32 lanes for
+        // the quarter (w >> 2) of the columns. Both groups accumulate into them for the whole kernel.
+        const int warp = threadIdx.x >> 5;
+        const uint32_t base = tmem + TM_WGRAD + 96u * (uint32_t)(warp >> 2) + ((uint32_t)(32 * (warp & 3)) << 16);
+#pragma unroll 1
+        for (int j = 0; j < 6; ++j) {
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+                         ::"r"(base + 16u * (uint32_t)j), "r"(0u) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        sctc::tc_fence_before();
+        __syncthreads();
+        sctc::tc_fence_after();
+    }
+
+    TileTC2 T;
+    tc2_init_tile(T, smem, blob, seq, seq_len, 5, 1);          // 5 operand buffers + 1 weight slot per group
+    T.tmem = tmem;
+    T.stash = stash_base + ((size_t)blockIdx.x * kGroups + T.g) * TS_PLANES_BWD * kStashPlane;
+    T.S = (MODE == 0) ? a.n_samples : 1;
+    T.rays_per_tile = (MODE == 0) ? MT / a.n_samples : MT;
+    T.beta = (MODE == 0) ? fabsf(*a.beta_param) + a.beta_min : 1.f;
+    const int tid = T.tg, lane = T.lane, r = T.row, ch = T.ch, c0 = NC * T.ch;     // tid: index inside the group
+    const bool issuer = T.issuer;
+    float* st = T.stash;
+    auto wgrad = [&](int m, const uint8_t* L, const uint8_t* R) { issue_wgrad(wg_taddr(T.tmem, m), L, R); };      // issuer only
+    // all threads of the group: make the operand stores visible to the tensor core and line the group up (no weights involved)
+    auto publish = [&]() { T.publish(); };
+    // wait until every MMA this group has issued so far (layer GEMMs and weight gradients) has completed
+    auto drain_mma = [&]() {
+        T.commit();
+        mbar_wait(T.mma_done, T.mma_phase); T.mma_phase ^= 1; sctc::tc_fence_after();
+        if (issuer) T.wr.prefetch();
+    };
+
+    const int per_tile = (MODE == 0) ? T.rays_per_tile : MT;
+    const int tiles_per_image = (a.n_per_image + per_tile - 1) / per_tile;
+    const int total = a.batch * tiles_per_image;
+    const int cb_rows = a.detach_latent ? CB_C0D : CB_C0;
+    float v[NC], h[NC], w1[NC], w2[NC];
+
+    const int first_tile = kGroups * blockIdx.x + T.g;
+    if (first_tile < total) {
+        T.wr.prologue(issuer);
+        for (int tile = first_tile; tile < total; tile += kGroups * gridDim.x) {
+            T.b = tile / tiles_per_image;
+            T.first = (tile % tiles_per_image) * per_tile;
+            float* cbb = a.cb_bar + (size_t)T.b * kCbRows * 64;
+            T.sync();
+            tc2_tile_setup<MODE>(T, a);
+            tc2_tile_forward<MODE, true>(T, a, second, MODE == 0);
+
+            // ================================================================================ upstream + ray phase
+            if (tid < MT) { T.pv(PV_XTB0)[tid] = 0.f; T.pv(PV_XTB1)[tid] = 0.f; T.pv(PV_XTB2)[tid] = 0.f; }
+            if (MODE == 1) {
+                if (tid < MT) {
+                    const int n = T.first + tid;
+                    const bool valid = n < a.n_per_image;
+                    const size_t g = (size_t)T.b * a.n_per_image + n;
+                    T.pv(PV_SDFB)[tid] = (valid && a.sdf_bar) ? a.sdf_bar[g] : 0.f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) T.pv(PV_GXB0 + c)[tid] = (valid && second) ? a.grad_bar[g * 3 + c] : 0.f;
+                }
+                T.sync();
+            } else {
+                ray2_phase_backward(T, a, vacc + VA_BETA);
+
+                // ============================================================================ RGB backward
+                if (tid < MT) {                                  // o3_bar = colour_bar * col (1 - col)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float col = T.pv(PV_COL0 + c)[tid];
+                        const float vv = T.pv(PV_CB0 + c)[tid] * col * (1.f - col);
+                        T.pv(PV_CB0 + c)[tid] = vv;
+                        const float sres = warp_sum(vv);
+                        if (lane == 0) atomicAdd(vacc + VA_C3R + c, sres);
+                    }
+                }
+                T.sync();
+                // o2_bar = (V3^T o3_bar) * [r2 > 0] -> Y ; dV3 += o3_bar (x) r2
+                st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);
+                {
+                    const float o0 = T.pv(PV_CB0)[r], o1 = T.pv(PV_CB1)[r], o2 = T.pv(PV_CB2)[r];
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const int k = c0 + i;
+                        const float t = T.cst[C_V3 + k] * o0 + T.cst[C_V3 + 64 + k] * o1 + T.cst[C_V3 + 128 + k] * o2;
+                        v[i] = h[i] > 0.f ? t : 0.f;
+                        w1[i] = o0 * h[i]; w2[i] = o1 * h[i]; h[i] = o2 * h[i];
+                    }
+                    colsum_shared(vacc + VA_V3, w1, ch, lane); colsum_shared(vacc + VA_V3 + 64, w2, ch, lane);
+                    colsum_shared(vacc + VA_V3 + 128, h, ch, lane);
+                }
+                row_store(T.Y(), r, ch, v);
+                colsum_shared(vacc + VA_C2R, v, ch, lane);
+                plane_to_act(T, st + (TS_R + 1) * kStashPlane, T.Z(), h);      // r1 -> Z (h keeps this thread's r1 values)
+                T.gemm(TM_ACC0, T.Y(), false);                                   // V2T : r1_bar = V2^T o2_bar
+                T.commit();                                                      // the epilogue overlaps the weight-gradient MMAs
+                if (issuer) wgrad(WG_V2, T.Y(), T.Z());
+                T.wait_and_load(TM_ACC0, v);
+#pragma unroll
+                for (int i = 0; i < NC; ++i) v[i] = h[i] > 0.f ? v[i] : 0.f;
+                row_store(T.X(), r, ch, v);                                      // o1_bar -> X
+                colsum_shared(vacc + VA_C1R, v, ch, lane);
+                plane_to_act(T, st + (TS_R + 0) * kStashPlane, T.U(), h);      // r0 -> U
+                T.gemm(TM_ACC0, T.X(), false);                                   // V1T
+                T.commit();
+                if (issuer) wgrad(WG_V1, T.X(), T.U());
+                T.wait_and_load(TM_ACC0, v);
+#pragma unroll
+                for (int i = 0; i < NC; ++i) v[i] = h[i] > 0.f ? v[i] : 0.f;
+                row_store(T.Z(), r, ch, v);                                      // o0_bar -> Z  (Z: wgrad V2 completed with the V1T phase)
+                colsum_global(cbb + CB_RGB * 64, v, ch, lane);
+                plane_to_act(T, st + TS_FEAT * kStashPlane, T.Y(), h);         // feat -> Y
+                T.gemm(TM_ACC0, T.Z(), false);                                   // V0FT -> feat_bar
+                T.gemm(TM_ACC1, T.Z(), false);                                   // V0PT -> pe_bar (rgb)
+                T.commit();
+                if (issuer) { wgrad(WG_V0F, T.Z(), T.Y()); wgrad(WG_V0P, T.Z(), T.P()); }
+                T.wait_and_load(TM_ACC0, v);
+                st_store(st + TS_FB * kStashPlane, r, ch, v);
+                colsum_shared(vacc + VA_B5F, v, ch, lane);
+                T.load_acc(TM_ACC1, v);
+                fold_pe_tc(T, v);
+                T.sync();
+            }
+
+            // ================================================================================ second-order sweep
+            if (second) {
+                // gpe_bar = J (S gx_bar) -> X ; x~_bar += S gx_bar * sum_k d2pe_k gpe_k
+                st_load(st + TS_GPE * kStashPlane, r, ch, h);
+                {
+                    const float gb[3] = {T.pv(PV_GXB0)[r] * T.pv(PV_SGN)[r], T.pv(PV_GXB1)[r], T.pv(PV_GXB2)[r]};
+                    float curv[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const int k = c0 + i;
+                        if (k < NPE) {
+                            v[i] = gb[k % 3] * dpe_tc(T.P(), k, r);
+                            curv[k % 3] = fmaf(d2pe_tc(T.P(), k, r), h[i], curv[k % 3]);
+                        } else v[i] = 0.f;
+                    }
+                    if (c0 < NPE) {
+                        atomicAdd(T.pv(PV_XTB0) + r, gb[0] * curv[0]); atomicAdd(T.pv(PV_XTB1) + r, gb[1] * curv[1]);
+                        atomicAdd(T.pv(PV_XTB2) + r, gb[2] * curv[2]);
+                    }
+                }
+                row_store(T.X(), r, ch, v);                                      // X = gpe_bar for the whole sweep
+                // layers 0..3: g_l_bar = A_l gpe_bar (+ B_l q_{l-1}_bar) ; q_l_bar = g_l_bar s_l ; SB_l = g_l_bar q_l ; g_l = q_l s_l
+                //   buffers: q_bar alternates Y, U, Y, U ; g_l always -> Z
+#pragma unroll 1
+                for (int l = 0; l < 4; ++l) {
+                    uint8_t* qprev = (l & 1) ? T.Y() : T.U();                    // q_{l-1}_bar (l >= 1)
+                    uint8_t* qcur = (l & 1) ? T.U() : T.Y();
+                    if (l < 3) {
+                        T.gemm(TM_ACC0, T.X(), false);                           // A0N | A1N | A2N
+                        if (l >= 1) T.gemm(TM_ACC0, qprev, true);                // B1N | B2N
+                    } else {
+                        T.gemm(TM_ACC0, qprev, false);                           // W3N
+                    }
+                    st_load(st + (TS_H + l) * kStashPlane, r, ch, h);
+                    st_load(st + (TS_Q + l) * kStashPlane, r, ch, w1);
+                    T.finish_and_load(TM_ACC0, v);
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) {
+                        const float s = sp_slope(h[i]);
+                        w2[i] = v[i] * w1[i];            // SB_l
+                        h[i] = w1[i] * s;                // g_l
+                        v[i] = v[i] * s;                 // q_l_bar
+                    }
+                    st_store(st + (TS_SB + l) * kStashPlane, r, ch, w2);
+                    row_store(qcur, r, ch, v); row_store(T.Z(), r, ch, h);
+                    publish();
+                    if (issuer) {
+                        if (l < 3) wgrad(l == 0 ? WG_A0 : (l == 1 ? WG_A1 : WG_A2), T.Z(), T.X());
+                        if (l == 1) wgrad(WG_B1, T.Z(), qprev);
+                        if (l == 2) wgrad(WG_B2, T.Z(), qprev);
+                        if (l == 3) wgrad(WG_W3, T.Z(), qprev);
+                    }
+                    // Z (g_l) and qprev are re-written in the next iteration's epilogue, i.e. after its finish_and_load,
+                    // whose commit covers these weight-gradient MMAs.
+                }
+                // layer 4 (q4 = w5): q3_bar is in U
+                T.gemm(TM_ACC0, T.U(), false);                                   // W4N
+                st_load(st + (TS_H + 4) * kStashPlane, r, ch, h);
+                T.finish_and_load(TM_ACC0, v);
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    const float s = sp_slope(h[i]);
+                    const float w5 = T.cst[C_W5 + c0 + i];
+                    w2[i] = v[i] * w5;                   // SB4
+                    w1[i] = v[i] * s;                    // -> dw5
+                    h[i] = w5 * s;                       // g4
+                }
+                st_store(st + (TS_SB + 4) * kStashPlane, r, ch, w2);
+                colsum_shared(vacc + VA_W5, w1, ch, lane);
+                row_store(T.Z(), r, ch, h);
+                publish();
+                if (issuer) wgrad(WG_W4, T.Z(), T.U());
+            }
+
+            // ================================================================================ first-order sweep
+            // a4_bar = (w5 sdf_bar + W5f^T feat_bar) s4 + SB4 t4 -> Y
+            if (MODE == 0) {
+                plane_to_act(T, st + TS_FB * kStashPlane, T.X(), v);           // feat_bar -> X (X = gpe_bar: its readers are done
+                T.gemm(TM_ACC0, T.X(), false);                                   //   once the W4N phase above completed)  W5FT
+                st_load(st + (TS_H + 4) * kStashPlane, r, ch, h);
+                if (second) st_load(st + (TS_SB + 4) * kStashPlane, r, ch, w2);
+                T.finish_and_load(TM_ACC0, v);
+            } else {
+                drain_mma();                                                     // mode 1: no GEMM here; retire the weight gradients
+                st_load(st + (TS_H + 4) * kStashPlane, r, ch, h);
+                if (second) st_load(st + (TS_SB + 4) * kStashPlane, r, ch, w2);
+#pragma unroll
+                for (int i = 0; i < NC; ++i) v[i] = 0.f;
+            }
+            {
+                const float sb = T.pv(PV_SDFB)[r];
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    float s, t;
+                    sp_slope_curv(h[i], s, t);
+                    const float hb = v[i] + T.cst[C_W5 + c0 + i] * sb;
+                    v[i] = hb * s + (second ? w2[i] * t : 0.f);      // a4_bar
+                    w1[i] = sb * h[i];                                // -> dw5
+                }
+                {   // db5 = sum of sdf_bar over the rows: column group 0 carries each row once (ch is per lane here)
+                    const float sres = warp_sum(ch == 0 ? sb : 0.f);
+                    if (lane == 0 && T.wg < 4) atomicAdd(vacc + VA_B5, sres);
+                }
+            }
+            row_store(T.Y(), r, ch, v);
+            colsum_shared(vacc + VA_B4, v, ch, lane);
+            colsum_shared(vacc + VA_W5, w1, ch, lane);
+            if (MODE == 0) {
+                row_store(T.Z(), r, ch, h);                                      // h4 -> Z  (Z = g4: weight gradient W4 retired above)
+                publish();
+                if (issuer) wgrad(WG_W5F, T.X(), T.Z());
+            }
+            // layers 3..0: dW_{l+1} += a_{l+1}_bar (x) h_l ; a_l_bar = (W_{l+1}^T a_{l+1}_bar) s_l + SB_l t_l
+            //   a_bar alternates Y -> X -> Y -> X -> Y ; h_l is loaded into U / Z alternately
+#pragma unroll 1
+            for (int l = 3; l >= 0; --l) {
+                uint8_t* acur = (l & 1) ? T.Y() : T.X();                         // a_{l+1}_bar
+                uint8_t* anew = (l & 1) ? T.X() : T.Y();                         // a_l_bar
+                uint8_t* hbuf = (l & 1) ? T.U() : T.Z();
+                plane_to_act(T, st + (TS_H + l) * kStashPlane, hbuf, h);        // h_l (h keeps this thread's values)
+                if (l < 2) { T.gemm(TM_ACC1, acur, false); }                     // A2T | A1T  -> pe_bar
+                T.gemm(TM_ACC0, acur, false);                                    // W4T | W3T | B2T | B1T
+                T.commit();
+                if (issuer) {
+                    wgrad(l == 3 ? WG_W4 : (l == 2 ? WG_W3 : (l == 1 ? WG_B2 : WG_B1)), acur, hbuf);
+                    if (l < 2) wgrad(l == 1 ? WG_A2 : WG_A1, acur, T.P());
+                }
+                if (second) st_load(st + (TS_SB + l) * kStashPlane, r, ch, w2);
+                T.wait_and_load(TM_ACC0, v);
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    float s, t;
+                    sp_slope_curv(h[i], s, t);
+                    v[i] = v[i] * s + (second ? w2[i] * t : 0.f);
+                }
+                row_store(anew, r, ch, v);
+                if (l == 3) colsum_shared(vacc + VA_B3, v, ch, lane);
+                else colsum_global(cbb + (cb_rows + l) * 64, v, ch, lane);
+                if (l < 2) {
+                    T.load_acc(TM_ACC1, w1);
+                    fold_pe_tc(T, w1);
+                }
+            }
+            // a0_bar is in Y: dA0 += a0_bar (x) pe ; pe_bar += A0^T a0_bar
+            T.gemm(TM_ACC1, T.Y(), false);                                       // A0T
+            if (issuer) wgrad(WG_A0, T.Y(), T.P());
+            T.finish_and_load(TM_ACC1, w1);
+            fold_pe_tc(T, w1);
+            T.sync();
+
+            // ================================================================================ x_bar -> outputs
+            if (MODE == 1) {
+                if (tid < MT) {
+                    const int n = T.first + tid;
+                    if (n < a.n_per_image && a.points_bar != nullptr) {
+                        const size_t g = ((size_t)T.b * a.n_per_image + n) * 3;
+                        a.points_bar[g + 0] = T.pv(PV_XTB0)[tid] * T.pv(PV_SGN)[tid];
+                        a.points_bar[g + 1] = T.pv(PV_XTB1)[tid];
+                        a.points_bar[g + 2] = T.pv(PV_XTB2)[tid];
+                    }
+                }
+            } else if (tid < MT) {
+                const int p = tid, S = T.S, rl = p / S, rr = T.first + rl;
+                const bool valid = rr < a.n_per_image;
+                const float xb0 = T.pv(PV_XTB0)[p] * T.pv(PV_SGN)[p], xb1 = T.pv(PV_XTB1)[p], xb2 = T.pv(PV_XTB2)[p];
+                const float z = T.pv(PV_Z)[p];
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+                if (valid) {
+                    const float* d = a.ray_dirs + ((size_t)T.b * a.n_per_image + rr) * 3;
+                    d0 = d[0]; d1 = d[1]; d2 = d[2];
+                }
+                const float zb = T.pv(PV_ZB)[p] + d0 * xb0 + d1 * xb1 + d2 * xb2;
+                float vv[7] = {xb0, xb1, xb2, z * xb0, z * xb1, z * xb2, zb};
+                const int seg = S < 32 ? S : 32;
+#pragma unroll
+                for (int q = 0; q < 7; ++q) vv[q] = seg_sum(vv[q], seg);
+                if ((lane & (seg - 1)) == 0 && valid) {
+                    float* db = a.ray_dirs_bar + ((size_t)T.b * a.n_per_image + rr) * 3;
+                    if (S <= 32) { db[0] = vv[3]; db[1] = vv[4]; db[2] = vv[5]; }
+                    else { atomicAdd(db + 0, vv[3]); atomicAdd(db + 1, vv[4]); atomicAdd(db + 2, vv[5]); }
+                    atomicAdd(a.cam_loc_bar + T.b * 3 + 0, vv[0]);
+                    atomicAdd(a.cam_loc_bar + T.b * 3 + 1, vv[1]);
+                    atomicAdd(a.cam_loc_bar + T.b * 3 + 2, vv[2]);
+                    atomicAdd(a.scale_dist_bar + T.b, a.cam_dist * vv[6]);
+                }
+            }
+        }
+        // retire this group's weight-gradient MMAs (no prefetch any more), then the weight copy still in flight
+        T.commit();
+        mbar_wait(T.mma_done, T.mma_phase); T.mma_phase ^= 1; sctc::tc_fence_after();
+        T.wr.drain(issuer);
+    }
+    sctc::tc_fence_before();
+    __syncthreads();                 // both groups are done: every weight-gradient MMA has completed (drain_mma above)
+    sctc::tc_fence_after();
+    {
+        // ---- flush: 12 TMEM-resident weight gradients + the shared vector accumulators -> this CTA's partial. All 16 warps,
+        // generation-1 mapping: TMEM lane quarter = warp & 3, 16 columns at 16 (warp >> 2); the M = 64 accumulators keep
+        // output row o of matrix m at lane 32 (o / 16) + 16 (m & 1) + o % 16.
+        const int warp = threadIdx.x >> 5, fl = threadIdx.x & 31, fc0 = NC * (warp >> 2);
+        float v[NC];
+        const int goff[NWG] = {G_A0, G_A1, G_A2, G_B1, G_B2, G_W3, G_W4, G_W5F, G_V0P, G_V0F, G_V1, G_V2};
+#pragma unroll 1
+        for (int pr = 0; pr < NWG / 2; ++pr) {
+            sct::tmem_ld_32x16(tmem + TM_WGRAD + 64u * (uint32_t)pr + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)fc0, v);
+            const int m = 2 * pr + (fl >> 4);
+            const int o = 16 * (warp & 3) + (fl & 15);
+            const bool narrow = (m == WG_A0 || m == WG_A1 || m == WG_A2 || m == WG_V0P);
+            const int ld = narrow ? NPE : 64;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                const int col = fc0 + i;
+                if (col < ld) part[goff[m] + o * ld + col] = v[i];
+            }
+        }
+        for (int i = threadIdx.x; i < VA_FLOATS; i += kThreads) part[G_V3 + i] = vacc[i];
+    }
+    sctc::tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) sctc::tmem_dealloc<512>(tmem);
+}
+
+}  // namespace sct2
+
+extern "C" int sc_render_tc2_supported(int mode, int n_samples);
+
+extern "C" int sc_render_tc2_backward(const ScRenderArgs* a, cudaStream_t stream)
+{
+    if (a == nullptr || a->blob == nullptr || a->cb == nullptr || a->scratch == nullptr || a->grad_partial == nullptr ||
+        a->cb_bar == nullptr)
+        return (int)cudaErrorInvalidValue;
+    if (a->mode != 0 && a->mode != 1) return (int)cudaErrorInvalidValue;
+    if (!sc_render_tc2_supported(a->mode, a->n_samples)) return (int)cudaErrorInvalidValue;
+    if (a->mode == 0 && (a->beta_param == nullptr || !a->ray_dirs_bar || !a->depth_fac_bar || !a->cam_loc_bar || !a->scale_dist_bar))
+        return (int)cudaErrorInvalidValue;
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t err;
+    // always the full persistent grid: sc_render_grad_finalize reduces one partial per SM
+    if (a->mode == 0) {
+        err = cudaFuncSetAttribute(sct2::render_tc2_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sct2::kSmemBytes);
+        if (err != cudaSuccess) return (int)err;
+        sct2::render_tc2_bwd_kernel<0><<<sms, sct2::kThreads, sct2::kSmemBytes, stream>>>(*a, (float*)a->scratch);
+    } else {
+        err = cudaFuncSetAttribute(sct2::render_tc2_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sct2::kSmemBytes);
+        if (err != cudaSuccess) return (int)err;
+        sct2::render_tc2_bwd_kernel<1><<<sms, sct2::kThreads, sct2::kSmemBytes, stream>>>(*a, (float*)a->scratch);
+    }
+    return (int)cudaGetLastError();
+}

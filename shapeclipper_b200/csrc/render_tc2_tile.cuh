@@ -1,0 +1,330 @@
+// render_tc2_tile.cuh — per-tile FORWARD program of the two-chain tensor-core render kernels (shared by forward and backward).
+// Same algorithm as render_tc_tile.cuh / tests/kernel_model.py on a 64-point tile owned by one 8-warp group; see render_tc2.cuh.
+#pragma once
+#include "render_tc2.cuh"
+#include "render_tile.cuh"      // sgnf, density, seg_sum
+
+namespace sct2 {
+
+struct TileTC2 {
+    uint8_t* act[kNumAct];      // P X Y Z U plane pairs (64 rows)
+    float *cst, *pt, *ray, *bias;           // bias: [8][64] = sdf layers 0..4 (cb0 cb1 cb2 b3 b4), rgb layers 0..2 (cb3 c1r c2r)
+    float* stash;
+    WeightRing2 wr;
+    uint64_t* mma_done;
+    uint32_t mma_phase;
+    uint32_t tmem;              // TMEM base address
+    uint32_t tm_ld;             // lane field + column half of this warp's accumulator reads: ((32 q + 16 g) << 16) + 32 (wg >> 2)
+    uint32_t tm_d;              // lane field of this group's accumulators as MMA destination: (16 g) << 16
+    int tid, g, tg, lane, wg, row, ch;
+    bool issuer;
+    int b, first, S, rays_per_tile;
+    float beta;
+    __device__ __forceinline__ void mark() {}
+    __device__ __forceinline__ float* pv(int v) const { return pt + v * MT; }
+    __device__ __forceinline__ uint8_t* P() const { return act[0]; }
+    __device__ __forceinline__ uint8_t* X() const { return act[1]; }
+    __device__ __forceinline__ uint8_t* Y() const { return act[2]; }
+    __device__ __forceinline__ uint8_t* Z() const { return act[3]; }
+    __device__ __forceinline__ uint8_t* U() const { return act[4]; }
+    __device__ __forceinline__ void sync() const { group_sync(g); }
+
+    // issuer: commit the phase's layer GEMMs. MMAs issued AFTER this (weight gradients) are covered by the NEXT phase's
+    // commit: their operand buffers must stay untouched until the next wait_and_load() has returned.
+    __device__ __forceinline__ void commit() { if (issuer) sctc::umma_commit(mma_done); }
+    __device__ __forceinline__ void finish_and_load(uint32_t acc_col, float (&v)[NC]) { commit(); wait_and_load(acc_col, v); }
+    // everyone in the group: wait for the accumulator, then read this thread's NC columns
+    __device__ __forceinline__ void wait_and_load(uint32_t acc_col, float (&v)[NC]) {
+        scr::mbar_wait(mma_done, mma_phase);
+        mma_phase ^= 1;
+        sctc::tc_fence_after();
+        if (issuer) wr.prefetch();
+        tmem_ld_16x32(tmem + acc_col + tm_ld, v);
+    }
+    __device__ __forceinline__ void load_acc(uint32_t acc_col, float (&v)[NC]) { tmem_ld_16x32(tmem + acc_col + tm_ld, v); }
+    // all threads of the group: publish the operand stores of the previous epilogue to the async proxy and line the group up
+    __device__ __forceinline__ void publish() { sctc::fence_proxy_async(); sctc::tc_fence_before(); sync(); sctc::tc_fence_after(); }
+    // one layer GEMM: publish, (issuer) wait for the weights, issue, release the slot
+    __device__ __forceinline__ void gemm(uint32_t acc_col, const uint8_t* a, bool accumulate) {
+        publish();
+        if (issuer) {
+            const uint8_t* w = wr.acquire_issuer();
+            issue_layer_gemm(tmem + acc_col + tm_d, a, w, accumulate);
+            wr.release_issuer();
+        }
+    }
+};
+
+// stash planes (floats, [64][64])
+constexpr int TS_H = 0, TS_Q = 5, TS_FEAT = 9, TS_R = 10, TS_GPE = 13, TS_FB = 14, TS_SB = 15, TS_PLANES_FWD = 5, TS_PLANES_BWD = 20;
+
+// d pe_k / d x~ for feature k of point p, from the posenc plane pair
+__device__ __forceinline__ float dpe_tc(const uint8_t* P, int k, int p) {
+    if (k < 3) return 1.f;
+    const int f = (k - 3) / 6, r = (k - 3) % 6;
+    const float fr = (float)(1 << f);
+    return (r < 3) ? fr * act_elem(P, p, k + 3) : -fr * act_elem(P, p, k - 3);
+}
+__device__ __forceinline__ float d2pe_tc(const uint8_t* P, int k, int p) {
+    if (k < 3) return 0.f;
+    const float fr = (float)(1 << ((k - 3) / 6));
+    return -fr * fr * act_elem(P, p, k);
+}
+
+template <int MODE>
+__device__ __forceinline__ void tc2_tile_setup(const TileTC2& T, const ScRenderArgs& a)
+{
+    // per-tile bias tables from the per-image latent biases cb [B][4][64]: sdf layers 0..2 and rgb layer 0
+    if (T.tg < 64) {
+        const float* cb = a.cb + (size_t)T.b * 256;
+        T.bias[0 * 64 + T.tg] = cb[0 * 64 + T.tg]; T.bias[1 * 64 + T.tg] = cb[1 * 64 + T.tg];
+        T.bias[2 * 64 + T.tg] = cb[2 * 64 + T.tg]; T.bias[5 * 64 + T.tg] = cb[3 * 64 + T.tg];
+    }
+    // every thread (row p, column group ch) derives the sample point of its row; group 0 publishes the per-point vectors
+    const int p = T.row;
+    float x0, x1, x2, z = 0.f;
+    bool valid;
+    if (MODE == 0) {
+        const int R = a.n_per_image, S = T.S;
+        const int r = T.first + p / S, s = p % S;
+        valid = r < R;
+        if (valid) {
+            const float c = __fmul_rn(a.cam_dist, a.scale_dist[T.b]);
+            const float nr = __fsub_rn(c, a.half_range), fr = __fadd_rn(c, a.half_range);
+            auto zb = [&](int i) {
+                const float t = a.t_vals[i];
+                return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.f, t)), __fmul_rn(fr, t));
+            };
+            z = zb(s);
+            if (a.jitter != nullptr) {
+                const float up = (s < S - 1) ? __fmul_rn(0.5f, __fadd_rn(zb(s + 1), z)) : z;
+                const float lo = (s > 0) ? __fmul_rn(0.5f, __fadd_rn(z, zb(s - 1))) : z;
+                const float u = a.jitter[((size_t)T.b * R + r) * S + s];
+                z = __fadd_rn(lo, __fmul_rn(__fsub_rn(up, lo), u));
+            }
+            const float* d = a.ray_dirs + ((size_t)T.b * R + r) * 3;
+            const float* o = a.cam_loc + (size_t)T.b * 3;
+            x0 = __fadd_rn(o[0], __fmul_rn(z, d[0]));
+            x1 = __fadd_rn(o[1], __fmul_rn(z, d[1]));
+            x2 = __fadd_rn(o[2], __fmul_rn(z, d[2]));
+        }
+    } else {
+        const int n = T.first + p;
+        valid = n < a.n_per_image;
+        if (valid) {
+            const float* q = a.points + ((size_t)T.b * a.n_per_image + n) * 3;
+            x0 = q[0]; x1 = q[1]; x2 = q[2];
+        }
+    }
+    if (!valid) { x0 = 0.25f; x1 = 0.25f; x2 = 0.25f; z = 0.f; }
+    if (T.ch == 0) {
+        T.pv(scr::PV_Z)[p] = z;
+        T.pv(scr::PV_SGN)[p] = scr::sgnf(x0);
+        T.pv(scr::PV_X0)[p] = x0; T.pv(scr::PV_X1)[p] = x1; T.pv(scr::PV_X2)[p] = x2;
+    }
+    const float xt[3] = {fabsf(x0), x1, x2};
+    // posenc: accurate sincosf at 2^0 and 2^3, angle doubling (sin 2a = 2 s c, cos 2a = 1 - 2 s^2) for the two octaves after
+    // each anchor: error growth 4x at most (~2.5e-7), well below the hi/lo-bf16 operand rounding of this path.
+    float v[NC];
+    const int k0 = NC * T.ch;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = (k0 + i < 3) ? xt[(k0 + i) % 3] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float sn, cs;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) {
+            if (f == 0) sincosf(xt[c], &sn, &cs);
+            else if (f == 3) sincosf(xt[c] * 8.f, &sn, &cs);
+            else { const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn; sn = s2; cs = c2; }
+            const int ks = 3 + 6 * f + c - k0, kc = ks + 3;              // columns of sin / cos relative to this thread's group
+#pragma unroll
+            for (int i = 0; i < NC; ++i) { if (i == ks) v[i] = sn; if (i == kc) v[i] = cs; }
+        }
+    }
+    row_store(T.P(), p, T.ch, v);
+}
+
+// Forward program (4 operand buffers: P, X, Y, Z). End state (mode 0): P = posenc, Y = g2, X = g1, Z = g0, per-point vectors SDF, COL*, GX*, SIG, CF, UN, NS*; (STASH_ALL) stash
+// planes H0..4, Q0..3, FEAT, R0..2, GPE.
+template <int MODE, bool STASH_ALL>
+__device__ __forceinline__ void tc2_tile_forward(TileTC2& T, const ScRenderArgs& a, bool want_grad, bool want_feat)
+{
+    using namespace scr;
+    const int r = T.row, ch = T.ch, c0 = NC * T.ch;
+    float v[NC], h[NC];
+    float* st = T.stash;
+
+    // ---- F.0 .. F.4: h_l = softplus(W_l [h_{l-1}; pe] + bias_l)      (a REAL loop: one copy of the epilogue code)
+#pragma unroll 1
+    for (int l = 0; l < 5; ++l) {
+        const uint8_t* src = (l == 0) ? T.P() : ((l & 1) ? T.X() : T.Y());
+        uint8_t* dst = (l & 1) ? T.Y() : T.X();
+        T.gemm(TM_ACC0, src, false);                                                     // A0N | B1N | B2N | W3N | W4N
+        if (l == 1 || l == 2) T.gemm(TM_ACC0, T.P(), true);                              // A1N | A2N
+        T.finish_and_load(TM_ACC0, v);
+        const float* bl = T.bias + l * 64 + c0;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] = softplus100(v[i] + bl[i]);
+        if (l == 4) {
+            float dot = 0.f;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) dot = fmaf(T.cst[C_W5 + c0 + i], v[i], dot);
+            T.pv(PX_A + ch)[r] = dot;                                                    // sdf partial (4 column groups)
+        }
+        row_store(dst, r, ch, v); st_store(st + (TS_H + l) * kStashPlane, r, ch, v);     // h4 ends in X
+    }
+    // ---- F.5 feat
+    if (MODE == 0 || want_feat) {
+        T.gemm(TM_ACC0, T.X(), false);                                                  // W5FN
+        T.finish_and_load(TM_ACC0, v);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] += T.cst[C_B5F + c0 + i];
+        if (MODE == 0) {
+            row_store(T.Z(), r, ch, v);
+            if (STASH_ALL) st_store(st + TS_FEAT * kStashPlane, r, ch, v);
+        } else if (a.feat != nullptr) {
+            const int n = T.first + r;
+            if (n < a.n_per_image) {
+                float4* dstg = reinterpret_cast<float4*>(a.feat + ((size_t)T.b * a.n_per_image + n) * 64 + c0);
+#pragma unroll
+                for (int q = 0; q < NC / 4; ++q) dstg[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+        }
+    }
+    if (MODE == 0) {
+        // ---- RGB.0 .. RGB.2 (+ the 3-wide output layer as per-thread partial dots)
+#pragma unroll 1
+        for (int l = 0; l < 3; ++l) {
+            const uint8_t* src = (l == 0) ? T.P() : ((l == 1) ? T.Y() : T.X());
+            uint8_t* dst = (l == 1) ? T.X() : T.Y();
+            T.gemm(TM_ACC0, src, false);                                                 // V0PN | V1N | V2N
+            if (l == 0) T.gemm(TM_ACC0, T.Z(), true);                                    // V0FN
+            T.finish_and_load(TM_ACC0, v);
+            const float* bl = T.bias + (5 + l) * 64 + c0;
+#pragma unroll
+            for (int i = 0; i < NC; ++i) v[i] = fmaxf(v[i] + bl[i], 0.f);
+            if (l == 2) {
+                float o0 = 0.f, o1 = 0.f, o2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < NC; ++i) {
+                    o0 = fmaf(T.cst[C_V3 + c0 + i], v[i], o0);
+                    o1 = fmaf(T.cst[C_V3 + 64 + c0 + i], v[i], o1);
+                    o2 = fmaf(T.cst[C_V3 + 128 + c0 + i], v[i], o2);
+                }
+                T.pv(PX_B + ch)[r] = o0; T.pv(PX_C + ch)[r] = o1; T.pv(PX_D + ch)[r] = o2;
+            }
+            if (l < 2 || STASH_ALL) row_store(dst, r, ch, v);                            // r0 -> Y, r1 -> X, r2 -> Y (backward only)
+            if (STASH_ALL) st_store(st + (TS_R + l) * kStashPlane, r, ch, v);
+        }
+    }
+    T.sync();
+    if (T.tg < MT) {
+        const int p = T.tg;
+        auto sum4 = [&](int base) { return T.pv(base)[p] + T.pv(base + 1)[p] + T.pv(base + 2)[p] + T.pv(base + 3)[p]; };
+        T.pv(PV_SDF)[p] = T.cst[C_B5] + sum4(PX_A);
+        if (MODE == 0) {
+            T.pv(PV_COL0)[p] = 1.f / (1.f + expf(-(T.cst[C_C3R + 0] + sum4(PX_B))));
+            T.pv(PV_COL1)[p] = 1.f / (1.f + expf(-(T.cst[C_C3R + 1] + sum4(PX_C))));
+            T.pv(PV_COL2)[p] = 1.f / (1.f + expf(-(T.cst[C_C3R + 2] + sum4(PX_D))));
+        }
+    }
+    if (MODE == 1 && !want_grad) { T.sync(); return; }
+
+    // ---- gradient pass. Stash reads are issued BEFORE waiting for the MMA so that their L2 latency overlaps it.
+    st_load(st + (TS_H + 4) * kStashPlane, r, ch, h);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = T.cst[C_W5 + c0 + i] * sp_slope(h[i]);
+    row_store(T.X(), r, ch, v);                                                          // g4 -> X
+#pragma unroll 1
+    for (int j = 3; j >= 0; --j) {                                                       // q_j = W_{j+1}^T g_{j+1}; g_j = q_j * s_j
+        const uint8_t* src = (j == 3) ? T.X() : ((j == 2) ? T.Z() : ((j == 1) ? T.Y() : T.X()));
+        uint8_t* dst = (j == 3) ? T.Z() : ((j == 2) ? T.Y() : ((j == 1) ? T.X() : T.Z()));   // g3->Z g2->Y g1->X g0->Z
+        T.gemm(TM_ACC0, src, false);                                                     // W4T | W3T | B2T | B1T
+        st_load(st + (TS_H + j) * kStashPlane, r, ch, h);
+        T.finish_and_load(TM_ACC0, v);
+        if (STASH_ALL) st_store(st + (TS_Q + j) * kStashPlane, r, ch, v);
+#pragma unroll
+        for (int i = 0; i < NC; ++i) v[i] *= sp_slope(h[i]);
+        row_store(dst, r, ch, v);
+    }
+    // gpe = A2^T g2 + A1^T g1 + A0^T g0  (accumulator 1)
+    T.gemm(TM_ACC1, T.Y(), false); T.gemm(TM_ACC1, T.X(), true); T.gemm(TM_ACC1, T.Z(), true);   // A2T, A1T, A0T
+    T.finish_and_load(TM_ACC1, v);
+    if (STASH_ALL) st_store(st + TS_GPE * kStashPlane, r, ch, v);
+    {   // gx~_c = sum_k gpe_k dpe_k : per-thread partial over this thread's columns
+        float g[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            const int k = c0 + i;
+            if (k < NPE) g[k % 3] = fmaf(v[i], dpe_tc(T.P(), k, r), g[k % 3]);
+        }
+        T.pv(PX_A + ch)[r] = g[0]; T.pv(PX_B + ch)[r] = g[1]; T.pv(PX_C + ch)[r] = g[2];
+    }
+    T.sync();
+    if (T.tg < MT) {
+        const int p = T.tg;
+        auto sum4 = [&](int base) { return T.pv(base)[p] + T.pv(base + 1)[p] + T.pv(base + 2)[p] + T.pv(base + 3)[p]; };
+        float g[3] = {sum4(PX_A) * T.pv(PV_SGN)[p], sum4(PX_B), sum4(PX_C)};
+        T.pv(PV_GX0)[p] = g[0]; T.pv(PV_GX1)[p] = g[1]; T.pv(PV_GX2)[p] = g[2];
+        if (MODE == 0) {
+            float sigma, cf, eh;
+            density(T.pv(PV_SDF)[p], T.beta, sigma, cf, eh);
+            const float u0 = cf * g[0], u1 = cf * g[1], u2 = cf * g[2];
+            const float un = sqrtf(u0 * u0 + u1 * u1 + u2 * u2);
+            const float inv = 1.f / fmaxf(un, 1e-12f);
+            T.pv(PV_SIG)[p] = sigma; T.pv(PV_CF)[p] = cf; T.pv(PV_UN)[p] = un;
+            T.pv(PV_NS0)[p] = u0 * inv; T.pv(PV_NS1)[p] = u1 * inv; T.pv(PV_NS2)[p] = u2 * inv;
+        }
+    }
+    T.sync();
+}
+
+// carve the shared memory of group g: n_act operand buffers then n_slots weight slots, all 16 KB
+__device__ __forceinline__ void tc2_init_tile(TileTC2& T, uint8_t* smem, const uint8_t* blob, const int8_t* seq, int seq_len,
+                                              int n_act, int n_slots)
+{
+    T.tid = threadIdx.x; T.g = threadIdx.x >> 8; T.tg = threadIdx.x & 255; T.lane = threadIdx.x & 31; T.wg = T.tg >> 5;
+    const int q = T.wg & 3, half = T.wg >> 2;
+    T.row = 16 * q + (T.lane & 15);
+    T.ch = 2 * half + (T.lane >> 4);
+    T.issuer = (T.tg == 0);
+    T.tm_ld = ((uint32_t)(32 * q + 16 * T.g) << 16) + (uint32_t)(32 * half);
+    T.tm_d = (uint32_t)(16 * T.g) << 16;
+    uint8_t* base = smem + (size_t)T.g * (n_act + n_slots) * kActBytes;
+    for (int i = 0; i < kNumAct; ++i) T.act[i] = base + (i < n_act ? i : n_act - 1) * kActBytes;
+    float* f = reinterpret_cast<float*>(smem + SMB_F32);
+    float* gf = f + SF_GROUP + T.g * GF_FLOATS;
+    T.cst = f + SF_CONST; T.bias = gf + GF_BIAS; T.pt = gf + GF_PT; T.ray = gf + GF_RAY;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMB_BAR) + T.g * 5;
+    T.wr.blob = blob; T.wr.slots = base + n_act * kActBytes; T.wr.wfull = bars; T.wr.wfree = bars + 2;
+    T.wr.seq = seq; T.wr.seq_len = seq_len; T.wr.NS = n_slots;
+    T.mma_done = bars + 4; T.mma_phase = 0;
+}
+
+// kernel prologue shared by forward and backward: barriers, TMEM, constants, constant bias rows of both groups
+__device__ __forceinline__ uint32_t tc2_prologue(uint8_t* smem, const uint8_t* blob)
+{
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMB_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 10; ++i) scr::mbar_init(bars + i, 1);
+        scr::mbar_fence_init();
+    }
+    if ((threadIdx.x >> 5) == 0) sctc::tmem_alloc<512>(tmem_slot);
+    float* f = reinterpret_cast<float*>(smem + SMB_F32);
+    const float* src = reinterpret_cast<const float*>(blob + sct::kTcConstOffsetBytes);
+    for (int i = threadIdx.x; i < scr::kConstFloats; i += kThreads) f[SF_CONST + i] = src[i];
+    for (int i = threadIdx.x; i < 2 * 64; i += kThreads) {       // constant rows of the bias tables: b3 b4 | c1r c2r
+        float* bias = f + SF_GROUP + (i >> 6) * GF_FLOATS + GF_BIAS;
+        const int c = i & 63;
+        bias[3 * 64 + c] = src[scr::C_B3 + c]; bias[4 * 64 + c] = src[scr::C_B4 + c];
+        bias[6 * 64 + c] = src[scr::C_C1R + c]; bias[7 * 64 + c] = src[scr::C_C2R + c];
+    }
+    sctc::tc_fence_before();
+    __syncthreads();
+    sctc::tc_fence_after();
+    return *tmem_slot;
+}
+
+}  // namespace sct2

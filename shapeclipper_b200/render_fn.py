@@ -9,26 +9,28 @@ from . import _render_native as rn
 
 _N_SDF, _N_RGB = 6, 4
 
-# Which generation of the render kernels runs: "tc" = tcgen05 tensor cores on hi/lo bf16 operand pairs (3 MMAs per
-# product, ~1e-5 relative), "fp32" = FP32 FFMA (the bit-for-bit-closest path). Both are CUDA kernels of this library.
+# Which generation of the render kernels runs: "tc2" / "tc" = tcgen05 tensor cores on hi/lo bf16 operand pairs (3 MMAs per
+# product, ~1e-5 relative; "tc2" = two independent 64-point tile chains per CTA, "tc" = one 128-point tile per CTA),
+# "fp32" = FP32 FFMA (the bit-for-bit-closest path). All are CUDA kernels of this library.
 import os as _os
-PRECISION = {"forward": _os.environ.get("SC_RENDER_FORWARD", "tc"), "backward": _os.environ.get("SC_RENDER_BACKWARD", "tc")}
+PRECISION = {"forward": _os.environ.get("SC_RENDER_FORWARD", "tc2"), "backward": _os.environ.get("SC_RENDER_BACKWARD", "tc2")}
 
 
 def set_precision(forward=None, backward=None):
     for k, v in (("forward", forward), ("backward", backward)):
         if v is not None:
-            if v not in ("tc", "fp32"):
-                raise ValueError("precision must be 'tc' or 'fp32'")
+            if v not in ("tc2", "tc", "fp32"):
+                raise ValueError("precision must be 'tc2', 'tc' or 'fp32'")
             PRECISION[k] = v
 
 
 def _fwd_tc():
-    return PRECISION["forward"] == "tc"
+    """False (FP32 FFMA) or the tensor-core generation name ("tc" / "tc2", both truthy)."""
+    return PRECISION["forward"] if PRECISION["forward"] in ("tc", "tc2") else False
 
 
 def _bwd_tc():
-    return PRECISION["backward"] == "tc" and hasattr(_lib.lib(), "sc_render_tc_backward")
+    return PRECISION["backward"] if PRECISION["backward"] in ("tc", "tc2") else False
 
 
 def _params_of(sdf_net, rgb_net, device):

@@ -11,10 +11,10 @@ from oracle import render_ref as R
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["tc", "fp32"])
+@pytest.fixture(autouse=True, params=["tc2", "tc", "fp32"])
 def render_precision(request):
-    """Every test runs on both generations of the render kernels: "tc" (tcgen05 tensor cores on hi/lo bf16 operand pairs,
-    the default) and "fp32" (FP32 FFMA)."""
+    """Every test runs on all generations of the render kernels: "tc2" (tcgen05 tensor cores on hi/lo bf16 operand pairs, two
+    64-point tile chains per CTA; the default), "tc" (one 128-point tile per CTA) and "fp32" (FP32 FFMA)."""
     from shapeclipper_b200 import render_fn
     old = dict(render_fn.PRECISION)
     render_fn.set_precision(forward=request.param, backward=request.param)
