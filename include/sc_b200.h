@@ -27,7 +27,7 @@ typedef struct CUstream_st* cudaStream_t;
 #endif
 
 /* ABI version of this header; bumped whenever a signature changes. */
-#define SC_B200_ABI_VERSION 1
+#define SC_B200_ABI_VERSION 2
 int sc_abi_version(void);
 
 /* ---- chamfer3D ------------------------------------------------------------
@@ -100,6 +100,11 @@ typedef struct ScRenderArgs {
     float* scale_dist_bar;  /* [B]    (zeroed by caller; atomics) */
     float* points_bar;      /* [B,N,3] (mode 1) */
     void* scratch;          /* sc_render_scratch_bytes() */
+    /* mode 0, tensor-core kernels (sc_render_tc_forward / sc_render_tc_backward), optional: a buffer of
+     * sc_render_tc_saved_bytes(batch, n_per_image, n_samples) bytes. Forward: the per-point activations the backward
+     * needs (H, Q, FEAT, R, GPE planes + per-point vectors, 3.75 KB per sample point) are written to it. Backward: they are
+     * read back instead of recomputing the forward per tile (19 of its 45 GEMM phases). NULL = recompute, no memory. */
+    void* saved;
 } ScRenderArgs;
 
 size_t sc_render_blob_floats(void);
@@ -123,6 +128,7 @@ size_t sc_render_tc_blob_bytes(void);
 size_t sc_render_tc_scratch_bytes(int backward);
 int sc_render_tc_pack_weights(const float* const* w, const float* const* b, const float* ffma_blob, void* tc_blob,
                               cudaStream_t stream);
+size_t sc_render_tc_saved_bytes(int batch, int n_per_image, int n_samples);
 int sc_render_tc_forward(const ScRenderArgs* args, cudaStream_t stream);
 int sc_render_tc_backward(const ScRenderArgs* args, cudaStream_t stream);
 /* Second generation of the tensor-core kernels: two independent 64-point tile chains per CTA (csrc/render_tc2.cuh). Same

@@ -23,7 +23,7 @@ class ScRenderArgs(ctypes.Structure):
         ("rgb_bar", _fp), ("mask_bar", _fp), ("depth_bar", _fp), ("normal_bar", _fp), ("sdf_bar", _fp), ("grad_bar", _fp),
         ("grad_partial", _fp), ("cb_bar", _fp), ("ray_dirs_bar", _fp), ("depth_fac_bar", _fp), ("cam_loc_bar", _fp),
         ("scale_dist_bar", _fp), ("points_bar", _fp),
-        ("scratch", _fp),
+        ("scratch", _fp), ("saved", _fp),
     ]
 
 
@@ -45,6 +45,8 @@ def declare(L):
     L.sc_render_tc_scratch_bytes.restype = sz
     L.sc_render_tc_pack_weights.argtypes = [vp, vp, vp, vp, vp]
     L.sc_render_tc_pack_weights.restype = i
+    L.sc_render_tc_saved_bytes.argtypes = [i, i, i]
+    L.sc_render_tc_saved_bytes.restype = sz
     L.sc_render_tc_forward.argtypes = [ctypes.POINTER(ScRenderArgs), vp]
     L.sc_render_tc_forward.restype = i
     L.sc_render_tc2_supported.argtypes = [i, i]
@@ -169,6 +171,19 @@ def scratch(device, backward, tc=False):
     L = _lib.lib()
     with torch.cuda.device(device):
         n = (L.sc_render_tc_scratch_bytes if tc else L.sc_render_scratch_bytes)(1 if backward else 0)
+    return torch.empty(n // 4, dtype=torch.float32, device=device)
+
+
+SAVE_ACTIVATIONS_MAX_BYTES = 24 << 30     # per render; above this the backward recomputes the forward per tile instead
+
+
+def saved_buffer(device, batch, n_per_image, n_samples):
+    """Activation buffer the generation-1 tensor-core forward fills for its backward (ScRenderArgs.saved), or None when the
+    shape is not supported / too large (the backward then recomputes)."""
+    L = _lib.lib()
+    n = L.sc_render_tc_saved_bytes(int(batch), int(n_per_image), int(n_samples))
+    if n == 0 or n > SAVE_ACTIVATIONS_MAX_BYTES:
+        return None
     return torch.empty(n // 4, dtype=torch.float32, device=device)
 
 

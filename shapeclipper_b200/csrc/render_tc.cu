@@ -81,7 +81,8 @@ __device__ __forceinline__ void tc_init_tile_struct(TileTC& T, uint8_t* smem, co
     T.row = 32 * (T.warp & 3) + T.lane; T.ch = T.warp >> 2;
 }
 
-template <int MODE>
+// SAVE (mode 0 only): a.saved receives every tile's activation planes + per-point vectors for sc_render_tc_backward
+template <int MODE, bool SAVE>
 __global__ void __launch_bounds__(kThreads, 1) render_tc_fwd_kernel(const ScRenderArgs a, float* stash_base)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -133,9 +134,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_fwd_kernel(const ScRend
             T.first = (tile % tiles_per_image) * per_tile;
             __syncthreads();
             T.mark();
+            if (SAVE) T.stash = reinterpret_cast<float*>(a.saved) + (size_t)tile * TS_SAVED_PLANES * kStashPlane;
             tc_tile_setup<MODE>(T, a);
             T.mark();
-            tc_tile_forward<MODE, false>(T, a, want_grad, want_feat);
+            tc_tile_forward<MODE, SAVE>(T, a, want_grad, want_feat);
+            if (SAVE) saved_vectors<true>(T, T.stash + TS_SAVED_PV * kStashPlane);
             T.mark();
 
             if (MODE == 1) {
@@ -220,6 +223,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_fwd_kernel(const ScRend
 using namespace sct;
 
 extern "C" size_t sc_render_tc_blob_bytes(void) { return kTcBlobBytes; }
+extern "C" size_t sc_render_tc_saved_bytes(int batch, int n_per_image, int n_samples) {
+    if (batch <= 0 || n_per_image <= 0 || n_samples < 4 || n_samples > M_TILE || (M_TILE % n_samples) != 0) return 0;
+    const int per_tile = M_TILE / n_samples;
+    const size_t tiles = (size_t)batch * ((n_per_image + per_tile - 1) / per_tile);
+    return tiles * TS_SAVED_PLANES * kStashPlane * sizeof(float);
+}
 extern "C" size_t sc_render_tc_scratch_bytes(int backward) {
     int dev = 0, n = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
@@ -251,14 +260,18 @@ extern "C" int sc_render_tc_forward(const ScRenderArgs* a, cudaStream_t stream)
     const long total = (long)a->batch * ((a->n_per_image + per_tile - 1) / per_tile);
     const int grid = total < sms ? (int)total : sms;
     cudaError_t err;
-    if (a->mode == 0) {
-        err = cudaFuncSetAttribute(render_tc_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc);
+    if (a->mode == 0 && a->saved != nullptr) {
+        err = cudaFuncSetAttribute(render_tc_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc);
         if (err != cudaSuccess) return (int)err;
-        render_tc_fwd_kernel<0><<<grid, kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch);
+        render_tc_fwd_kernel<0, true><<<grid, kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch);
+    } else if (a->mode == 0) {
+        err = cudaFuncSetAttribute(render_tc_fwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc);
+        if (err != cudaSuccess) return (int)err;
+        render_tc_fwd_kernel<0, false><<<grid, kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch);
     } else {
-        err = cudaFuncSetAttribute(render_tc_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc);
+        err = cudaFuncSetAttribute(render_tc_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc);
         if (err != cudaSuccess) return (int)err;
-        render_tc_fwd_kernel<1><<<grid, kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch);
+        render_tc_fwd_kernel<1, false><<<grid, kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch);
     }
     return (int)cudaGetLastError();
 }

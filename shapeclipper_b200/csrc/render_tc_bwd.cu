@@ -16,13 +16,16 @@ namespace sct {
 
 using namespace scr;
 
-__device__ __forceinline__ void build_seq_tc_bwd(int8_t* seq, int& len, int mode, bool second)
+// recompute = false (mode 0 with saved activations): the tile program starts at the RGB backward
+__device__ __forceinline__ void build_seq_tc_bwd(int8_t* seq, int& len, int mode, bool second, bool recompute)
 {
     int n = 0;
-    const int8_t base[] = {A0N, B1N, A1N, B2N, A2N, W3N, W4N};
-    for (int i = 0; i < 7; ++i) seq[n++] = base[i];
-    if (mode == 0) { seq[n++] = W5FN; seq[n++] = V0PN; seq[n++] = V0FN; seq[n++] = V1N; seq[n++] = V2N; }
-    if (second) { const int8_t g[] = {W4T, W3T, B2T, B1T, A2T, A1T, A0T}; for (int i = 0; i < 7; ++i) seq[n++] = g[i]; }
+    if (recompute) {
+        const int8_t base[] = {A0N, B1N, A1N, B2N, A2N, W3N, W4N};
+        for (int i = 0; i < 7; ++i) seq[n++] = base[i];
+        if (mode == 0) { seq[n++] = W5FN; seq[n++] = V0PN; seq[n++] = V0FN; seq[n++] = V1N; seq[n++] = V2N; }
+        if (second) { const int8_t g[] = {W4T, W3T, B2T, B1T, A2T, A1T, A0T}; for (int i = 0; i < 7; ++i) seq[n++] = g[i]; }
+    }
     if (mode == 0) { seq[n++] = V2T; seq[n++] = V1T; seq[n++] = V0FT; seq[n++] = V0PT; }
     if (second) { const int8_t s2[] = {A0N, A1N, B1N, A2N, B2N, W3N, W4N}; for (int i = 0; i < 7; ++i) seq[n++] = s2[i]; }
     if (mode == 0) seq[n++] = W5FT;
@@ -101,13 +104,14 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
     const bool second = (MODE == 0) || (a.want_grad && a.grad_bar != nullptr);
+    const bool use_saved = (MODE == 0) && a.saved != nullptr;      // activations saved by sc_render_tc_forward: no recompute
     float* part = a.grad_partial + (size_t)blockIdx.x * kGradFloats;
     for (int i = threadIdx.x; i < kGradFloats; i += kThreads) part[i] = 0.f;
     for (int i = threadIdx.x; i < VA_FLOATS; i += kThreads) vacc[i] = 0.f;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 9; ++i) mbar_init(bars + i, 1);
         mbar_fence_init();
-        int len; build_seq_tc_bwd(seq, len, MODE, second); seq_len = len;
+        int len; build_seq_tc_bwd(seq, len, MODE, second, !use_saved); seq_len = len;
     }
     if ((threadIdx.x >> 5) == 0) sctc::tmem_alloc<512>(tmem_slot);
     {
@@ -143,7 +147,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
     T.rays_per_tile = (MODE == 0) ? M_TILE / a.n_samples : M_TILE;
     T.beta = (MODE == 0) ? fabsf(*a.beta_param) + a.beta_min : 1.f;
     const int tid = T.tid, lane = T.lane, r = T.row, ch = T.ch, c0 = NC * T.ch;
-    float* st = T.stash;
+    float* const sc = T.stash;            // per-CTA scratch planes (FB, SB: written and re-read inside one tile)
+    float* st = T.stash;                  // activation planes: the same scratch (recompute) or the tile's saved block
     uint32_t wg_init = 0;                 // thread 0: which weight-gradient accumulators already hold data
     auto wgrad = [&](int m, const uint8_t* L, const uint8_t* R) {      // thread 0 only
         issue_wgrad(wg_taddr(T.tmem, m), L, R, (wg_init >> m) & 1u);
@@ -171,7 +176,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
             float* cbb = a.cb_bar + (size_t)T.b * kCbRows * 64;
             __syncthreads();
             tc_tile_setup<MODE>(T, a);
-            tc_tile_forward<MODE, true>(T, a, second, MODE == 0);
+            if (use_saved) {
+                st = reinterpret_cast<float*>(a.saved) + (size_t)tile * TS_SAVED_PLANES * kStashPlane;
+                saved_vectors<false>(T, st + TS_SAVED_PV * kStashPlane);
+                __syncthreads();
+            } else {
+                tc_tile_forward<MODE, true>(T, a, second, MODE == 0);
+            }
 
             // ================================================================================ upstream + ray phase
             if (tid < M_TILE) { T.pv(PV_XTB0)[tid] = 0.f; T.pv(PV_XTB1)[tid] = 0.f; T.pv(PV_XTB2)[tid] = 0.f; }
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 T.commit();
                 if (tid == 0) { wgrad(WG_V0F, T.Z(), T.Y()); wgrad(WG_V0P, T.Z(), T.P()); }
                 T.wait_and_load(TM_ACC0, v);
-                st_store(st + TS_FB * kStashPlane, r, ch, v);
+                st_store(sc + TS_FB * kStashPlane, r, ch, v);
                 colsum_shared(vacc + VA_B5F, v, ch, lane);
                 tmem_ld_32x16(T.tmem + TM_ACC1 + ((uint32_t)(32 * (T.warp & 3)) << 16) + (uint32_t)c0, v);
                 fold_pe_tc(T, v);
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                         h[i] = w1[i] * s;                // g_l
                         v[i] = v[i] * s;                 // q_l_bar
                     }
-                    st_store(st + (TS_SB + l) * kStashPlane, r, ch, w2);
+                    st_store(sc + (TS_SB + l) * kStashPlane, r, ch, w2);
                     row_store(qcur, r, ch, v); row_store(T.Z(), r, ch, h);
                     publish();
                     if (tid == 0) {
@@ -314,7 +325,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                     w1[i] = v[i] * s;                    // -> dw5
                     h[i] = w5 * s;                       // g4
                 }
-                st_store(st + (TS_SB + 4) * kStashPlane, r, ch, w2);
+                st_store(sc + (TS_SB + 4) * kStashPlane, r, ch, w2);
                 colsum_shared(vacc + VA_W5, w1, ch, lane);
                 row_store(T.Z(), r, ch, h);
                 publish();
@@ -324,15 +335,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
             // ================================================================================ first-order sweep
             // a4_bar = (w5 sdf_bar + W5f^T feat_bar) s4 + SB4 t4 -> Y
             if (MODE == 0) {
-                plane_to_act(T, st + TS_FB * kStashPlane, T.X(), v);           // feat_bar -> X (X = gpe_bar: its readers are done
+                plane_to_act(T, sc + TS_FB * kStashPlane, T.X(), v);           // feat_bar -> X (X = gpe_bar: its readers are done
                 T.gemm(TM_ACC0, T.X(), false);                                   //   once the W4N phase above completed)  W5FT
                 st_load(st + (TS_H + 4) * kStashPlane, r, ch, h);
-                if (second) st_load(st + (TS_SB + 4) * kStashPlane, r, ch, w2);
+                if (second) st_load(sc + (TS_SB + 4) * kStashPlane, r, ch, w2);
                 T.finish_and_load(TM_ACC0, v);
             } else {
                 drain_mma();                                                     // mode 1: no GEMM here; retire the weight gradients
                 st_load(st + (TS_H + 4) * kStashPlane, r, ch, h);
-                if (second) st_load(st + (TS_SB + 4) * kStashPlane, r, ch, w2);
+                if (second) st_load(sc + (TS_SB + 4) * kStashPlane, r, ch, w2);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) v[i] = 0.f;
             }
@@ -371,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                     wgrad(l == 3 ? WG_W4 : (l == 2 ? WG_W3 : (l == 1 ? WG_B2 : WG_B1)), acur, hbuf);
                     if (l < 2) wgrad(l == 1 ? WG_A2 : WG_A1, acur, T.P());
                 }
-                if (second) st_load(st + (TS_SB + l) * kStashPlane, r, ch, w2);
+                if (second) st_load(sc + (TS_SB + l) * kStashPlane, r, ch, w2);
                 T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) {

@@ -55,6 +55,23 @@ struct TileTC {
 
 // stash planes (floats, row-major [128][64])
 constexpr int TS_H = 0, TS_Q = 5, TS_FEAT = 9, TS_R = 10, TS_GPE = 13, TS_FB = 14, TS_SB = 15, TS_PLANES_FWD = 5, TS_PLANES_BWD = 20;
+// saved-activation buffer (ScRenderArgs::saved), per tile: planes H0..4, Q0..3, FEAT, R0..2, GPE as above, then one plane of
+// per-point vectors [kSavedVecs][128]
+constexpr int TS_SAVED_PV = 14, TS_SAVED_PLANES = 15;
+constexpr int kSavedVecs = 13;
+// forward (store = true): per-point vectors the backward needs -> plane TS_SAVED_PV of the tile's saved block; backward: back.
+template <bool STORE>
+__device__ __forceinline__ void saved_vectors(const TileTC& T, float* plane) {
+    constexpr int vecs[kSavedVecs] = {scr::PV_SDF, scr::PV_COL0, scr::PV_COL1, scr::PV_COL2, scr::PV_GX0, scr::PV_GX1, scr::PV_GX2,
+                                      scr::PV_SIG, scr::PV_CF, scr::PV_UN, scr::PV_NS0, scr::PV_NS1, scr::PV_NS2};
+    if (T.tid < M_TILE) {
+#pragma unroll
+        for (int i = 0; i < kSavedVecs; ++i) {
+            if (STORE) __stcg(plane + i * M_TILE + T.tid, T.pv(vecs[i])[T.tid]);
+            else T.pv(vecs[i])[T.tid] = __ldcg(plane + i * M_TILE + T.tid);
+        }
+    }
+}
 
 // d pe_k / d x~ for feature k of point p, from the posenc plane pair
 __device__ __forceinline__ float dpe_tc(const uint8_t* P, int k, int p) {

@@ -13,7 +13,10 @@ _N_SDF, _N_RGB = 6, 4
 # product, ~1e-5 relative; "tc2" = two independent 64-point tile chains per CTA, "tc" = one 128-point tile per CTA),
 # "fp32" = FP32 FFMA (the bit-for-bit-closest path). All are CUDA kernels of this library.
 import os as _os
-PRECISION = {"forward": _os.environ.get("SC_RENDER_FORWARD", "tc2"), "backward": _os.environ.get("SC_RENDER_BACKWARD", "tc2")}
+PRECISION = {"forward": _os.environ.get("SC_RENDER_FORWARD", "tc"), "backward": _os.environ.get("SC_RENDER_BACKWARD", "tc")}
+
+
+SAVE_ACTIVATIONS = _os.environ.get("SC_RENDER_SAVE_ACTIVATIONS", "1") != "0"
 
 
 def set_precision(forward=None, backward=None):
@@ -111,9 +114,17 @@ class _RenderFn(torch.autograd.Function):
                          rgb=rgb, mask=mask, mask_hard=mask_hard, depth=depth, normal=normal, scratch=scratch)
         if jit is not None:
             args.jitter = ctypes.c_void_p(jit.data_ptr())
+        # generation-1 tensor-core kernels, some input needs a gradient: the forward saves its per-point activations
+        # (3.75 KB per sample point) and the backward reads them back instead of recomputing 19 of its 45 GEMM phases
+        saved = None
+        if tc == "tc" and _bwd_tc() == "tc" and SAVE_ACTIVATIONS and any(ctx.needs_input_grad):
+            saved = rn.saved_buffer(dev, B, R, cfg["n_samples"])
+            if saved is not None:
+                args.saved = ctypes.c_void_p(saved.data_ptr())
         rn.launch_forward(args, dev, tc=tc)
         ctx.cfg = cfg
         ctx.has_jitter = jit is not None
+        ctx.saved_acts = saved
         ctx.save_for_backward(blob, cb, beta_c, cam_loc, ray_dirs, depth_fac, scale_dist, t_vals,
                               jit if jit is not None else t_vals, f(z_sdf), f(z_rgb), *params)
         ctx.mark_non_differentiable(mask_hard)
@@ -151,7 +162,10 @@ class _RenderFn(torch.autograd.Function):
         for name, t in (("rgb_bar", rgb_bar), ("mask_bar", mask_bar), ("depth_bar", depth_bar), ("normal_bar", normal_bar)):
             if t is not None:
                 setattr(args, name, ctypes.c_void_p(t.data_ptr()))
+        if ctx.saved_acts is not None and tc == "tc":
+            args.saved = ctypes.c_void_p(ctx.saved_acts.data_ptr())
         rn.launch_backward(args, dev, tc=tc)
+        ctx.saved_acts = None
         gw, gb, z_sdf_bar, z_rgb_bar, beta_bar = _finalize(L, partial, n_ctas, cb_bar, z_sdf, z_rgb, blob, B, ws, bs, True)
         beta_param_bar = (beta_bar * torch.sign(beta_c)).reshape(())
         return (None, beta_param_bar, loc_bar, dirs_bar, fac_bar, sd_bar, z_sdf_bar, z_rgb_bar, None, None, *gw, *gb)

@@ -11,15 +11,18 @@ from oracle import render_ref as R
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["tc2", "tc", "fp32"])
+@pytest.fixture(autouse=True, params=["tc", "tc-recompute", "tc2", "fp32"])
 def render_precision(request):
     """Every test runs on all generations of the render kernels: "tc2" (tcgen05 tensor cores on hi/lo bf16 operand pairs, two
-    64-point tile chains per CTA; the default), "tc" (one 128-point tile per CTA) and "fp32" (FP32 FFMA)."""
+    64-point tile chains per CTA; selectable), "tc" (one 128-point tile per CTA; the default; with and without saved activations) and "fp32" (FP32 FFMA)."""
     from shapeclipper_b200 import render_fn
-    old = dict(render_fn.PRECISION)
-    render_fn.set_precision(forward=request.param, backward=request.param)
+    old, old_save = dict(render_fn.PRECISION), render_fn.SAVE_ACTIVATIONS
+    mode = request.param.split("-")[0]
+    render_fn.SAVE_ACTIVATIONS = request.param != "tc-recompute"     # "tc": the backward reads the forward's saved activations
+    render_fn.set_precision(forward=mode, backward=mode)
     yield request.param
     render_fn.set_precision(forward=old["forward"], backward=old["backward"])
+    render_fn.SAVE_ACTIVATIONS = old_save
 REL = 1e-4
 # Unit normals of grazing rays are ill-conditioned: on the golden fixtures the reference's own fp32 result is 1.8e-4
 # (mask 2e-3) to 1.8e-3 (mask 1e-4) away from an fp64 evaluation of the same inputs (measured with
