@@ -78,6 +78,8 @@ __device__ __forceinline__ void tc_init_tile_struct(TileTC& T, uint8_t* smem, co
     T.wr.seq = seq; T.wr.seq_len = seq_len; T.wr.NS = n_slots;
     T.mma_done = bars + 8; T.mma_phase = 0;
     T.tid = threadIdx.x; T.lane = threadIdx.x & 31; T.warp = threadIdx.x >> 5;
+    T.w0 = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0;          // warp-uniform for the compiler too
+    T.wr.w0 = T.w0;
     T.row = 32 * (T.warp & 3) + T.lane; T.ch = T.warp >> 2;
 }
 

@@ -168,38 +168,75 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {     //
     return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- MMA issue. Executed by ALL 32 lanes of the issuing warp (warp 0) with warp-uniform operands; one elected lane
+// executes the tcgen05.mma itself. (Issued from divergent `if (tid == 0)` code the compiler cannot keep the descriptors in
+// uniform registers and wraps EVERY MMA in an ELECT / 5x R2UR.BROADCAST / BRA.U.ANY loop: ~100 cycles per MMA against 32 of
+// tensor-pipe time — measured 1.3 k cycles of issue per 12-MMA layer GEMM on the critical path of every phase.)
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
+    return p != 0;
+}
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(sctc::smem_u32(bar)) : "memory");
+}
+// K-major / MN-major descriptors from a (warp-uniform) shared-memory byte address
+__device__ __forceinline__ uint64_t desc_k128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t desc_mn128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
 #ifdef SC_TC_NOINLINE_ISSUE          // the backward kernel (the forward kernel's loops keep its issue code cache-resident: inline is faster there)
 #define SC_TC_ISSUE_FN static __device__ __noinline__
 #else
 #define SC_TC_ISSUE_FN __device__ __forceinline__
 #endif
-// D[128 x 64] (+)= ACT[128 x 64] . W^T   (3 MMAs per 16-wide k-step). Issued by ONE thread.
+// D[128 x 64] (+)= ACT[128 x 64] . W^T   (3 MMAs per 16-wide k-step). Called by the whole issuing warp.
 // NOT inlined in the backward kernel (here and issue_wgrad): it has ~60 issue sites of 12-24 MMAs each; inlined they were 5 k
 // SASS instructions (25 % of the kernel) that the issuing warp walked once per tile, every line an instruction-cache miss
 // on the critical path of the phase (ncu: 29 % of the warp samples stalled on instruction fetch).
 SC_TC_ISSUE_FN void issue_layer_gemm(uint32_t tmem_d, const uint8_t* act, const uint8_t* w, bool accumulate) {
     constexpr uint32_t idesc = sctc::make_idesc_bf16(128, 64);
-    const uint64_t ah = sctc::make_smem_desc_k128(act), al = sctc::make_smem_desc_k128(act + kPlaneBytes);
-    const uint64_t wh = sctc::make_smem_desc_k128(w), wl = sctc::make_smem_desc_k128(w + kWPlaneBytes);
+    const uint32_t d = uniform_u32(tmem_d), acc = uniform_u32(accumulate ? 1u : 0u);
+    const uint32_t a0 = uniform_u32(sctc::smem_u32(act)), w0 = uniform_u32(sctc::smem_u32(w));
+    const uint64_t ah = desc_k128(a0), al = desc_k128(a0 + kPlaneBytes);
+    const uint64_t wh = desc_k128(w0), wl = desc_k128(w0 + kWPlaneBytes);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint64_t adv = (uint64_t)(2 * k);
-        sctc::umma_bf16(tmem_d, ah + adv, wh + adv, idesc, (accumulate || k > 0) ? 1u : 0u);
-        sctc::umma_bf16(tmem_d, ah + adv, wl + adv, idesc, 1u);
-        sctc::umma_bf16(tmem_d, al + adv, wh + adv, idesc, 1u);
+        umma_bf16_elect(d, ah + adv, wh + adv, idesc, k > 0 ? 1u : acc);
+        umma_bf16_elect(d, ah + adv, wl + adv, idesc, 1u);
+        umma_bf16_elect(d, al + adv, wh + adv, idesc, 1u);
     }
 }
-// D[64 x 64] += L^T . R over the tile's 128 points (L, R = plane pairs). Issued by ONE thread.
+// D[64 x 64] += L^T . R over the tile's 128 points (L, R = plane pairs). Called by the whole issuing warp.
 SC_TC_ISSUE_FN void issue_wgrad(uint32_t tmem_d, const uint8_t* L, const uint8_t* R, bool accumulate) {
     constexpr uint32_t idesc = make_idesc_bf16_mn(64, 64);
-    const uint64_t lh = make_smem_desc_mn128(L), ll = make_smem_desc_mn128(L + kPlaneBytes);
-    const uint64_t rh = make_smem_desc_mn128(R), rl = make_smem_desc_mn128(R + kPlaneBytes);
+    const uint32_t d = uniform_u32(tmem_d), acc = uniform_u32(accumulate ? 1u : 0u);
+    const uint32_t l0 = uniform_u32(sctc::smem_u32(L)), r0 = uniform_u32(sctc::smem_u32(R));
+    const uint64_t lh = desc_mn128(l0), ll = desc_mn128(l0 + kPlaneBytes);
+    const uint64_t rh = desc_mn128(r0), rl = desc_mn128(r0 + kPlaneBytes);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const uint64_t adv = (uint64_t)(k * (16 * 128 >> 4));          // 16 points = 16 rows of 128 B
-        sctc::umma_bf16(tmem_d, lh + adv, rh + adv, idesc, (accumulate || k > 0) ? 1u : 0u);
-        sctc::umma_bf16(tmem_d, lh + adv, rl + adv, idesc, 1u);
-        sctc::umma_bf16(tmem_d, ll + adv, rh + adv, idesc, 1u);
+        umma_bf16_elect(d, lh + adv, rh + adv, idesc, k > 0 ? 1u : acc);
+        umma_bf16_elect(d, lh + adv, rl + adv, idesc, 1u);
+        umma_bf16_elect(d, ll + adv, rh + adv, idesc, 1u);
     }
 }
 
@@ -214,43 +251,48 @@ struct WeightRing {
     int NS;
     uint32_t n;                   // matrices consumed
     int pos_fetch;                // position in seq of the next matrix to fetch
+    bool w0;                      // this thread belongs to the issuing warp (warp 0); its 32 lanes keep n / pos_fetch in step
 
+    // issuing warp, all lanes (state); one elected lane starts the copy
     __device__ __forceinline__ void issue(uint32_t idx) {
         const uint32_t s = idx % (uint32_t)NS;
-        uint64_t* bar = wfull + s;
-        scr::mbar_expect_tx(bar, kWSegBytes);
-        scr::tma_bulk_g2s(slots + s * kWSegBytes, blob + (size_t)seq[pos_fetch] * kWSegBytes, kWSegBytes, bar);
+        if (elect_one()) {
+            uint64_t* bar = wfull + s;
+            scr::mbar_expect_tx(bar, kWSegBytes);
+            scr::tma_bulk_g2s(slots + s * kWSegBytes, blob + (size_t)seq[pos_fetch] * kWSegBytes, kWSegBytes, bar);
+        }
+        __syncwarp();
         pos_fetch = (pos_fetch + 1 == seq_len) ? 0 : pos_fetch + 1;
     }
     __device__ __forceinline__ void prologue() {
         n = 0; pos_fetch = 0;
-        if (threadIdx.x == 0) for (int i = 0; i < NS - 1; ++i) issue((uint32_t)i);
+        if (w0) for (int i = 0; i < NS - 1; ++i) issue((uint32_t)i);
     }
     // all threads: publishes the operand stores of the previous epilogue to the async proxy, syncs the CTA and returns the
-    // slot of matrix n. Only thread 0 (the MMA issuer) waits for the weights to land.
+    // slot of matrix n. Only the issuing warp waits for the weights to land.
     __device__ __forceinline__ const uint8_t* acquire() {
         sctc::fence_proxy_async();
         sctc::tc_fence_before();
         __syncthreads();
         sctc::tc_fence_after();
         const uint32_t cur = n;
-        if (threadIdx.x == 0) scr::mbar_wait(wfull + (cur % NS), (cur / NS) & 1);
+        if (w0) scr::mbar_wait(wfull + (cur % NS), (cur / NS) & 1);
         n = cur + 1;
         return slots + (cur % NS) * kWSegBytes;
     }
-    // thread 0, AFTER issuing the MMAs that read the slot returned by the last acquire(): release that slot when they
+    // issuing warp, AFTER issuing the MMAs that read the slot returned by the last acquire(): release that slot when they
     // complete, then prefetch matrix n + NS - 2 into the slot of the matrix before it (waiting for ITS MMAs, which are
     // ahead of ours in the tensor pipe, so the wait overlaps useful work instead of delaying the issue).
     __device__ __forceinline__ void release() {
         const uint32_t cur = n - 1;
-        sctc::umma_commit(wfree + (cur % NS));
+        umma_commit_elect(wfree + (cur % NS));
         const uint32_t nx = cur + (uint32_t)NS - 1;
         if (cur >= 1) scr::mbar_wait(wfree + (nx % NS), ((nx / NS) - 1) & 1);
         issue(nx);
     }
     // NS - 1 copies are always in flight: wait for them before the CTA exits
     __device__ __forceinline__ void drain() {
-        if (threadIdx.x == 0)
+        if (w0)
             for (uint32_t m = n; m < n + (uint32_t)NS - 1; ++m) scr::mbar_wait(wfull + (m % NS), (m / NS) & 1);
         __syncthreads();
     }

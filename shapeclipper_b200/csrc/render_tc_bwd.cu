@@ -136,6 +136,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
         T.wr.seq = seq; T.wr.seq_len = seq_len; T.wr.NS = 2;
         T.mma_done = bars + 8; T.mma_phase = 0;
         T.tid = threadIdx.x; T.lane = threadIdx.x & 31; T.warp = threadIdx.x >> 5;
+        T.w0 = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0;      // the issuing warp, warp-uniform for the compiler too
+        T.wr.w0 = T.w0;
         T.row = 32 * (T.warp & 3) + T.lane; T.ch = T.warp >> 2;
 #ifdef SC_TC_TRACE
         T.trace = (MODE == 0) ? reinterpret_cast<long long*>(a.points_bar) : nullptr; T.trace_n = 0;
@@ -149,8 +151,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
     const int tid = T.tid, lane = T.lane, r = T.row, ch = T.ch, c0 = NC * T.ch;
     float* const sc = T.stash;            // per-CTA scratch planes (FB, SB: written and re-read inside one tile)
     float* st = T.stash;                  // activation planes: the same scratch (recompute) or the tile's saved block
-    uint32_t wg_init = 0;                 // thread 0: which weight-gradient accumulators already hold data
-    auto wgrad = [&](int m, const uint8_t* L, const uint8_t* R) {      // thread 0 only
+    const bool w0 = T.w0;
+    uint32_t wg_init = 0;                 // issuing warp: which weight-gradient accumulators already hold data
+    auto wgrad = [&](int m, const uint8_t* L, const uint8_t* R) {      // issuing warp only (all 32 lanes)
         issue_wgrad(wg_taddr(T.tmem, m), L, R, (wg_init >> m) & 1u);
         wg_init |= 1u << m;
     };
@@ -158,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
     auto publish = [&]() { sctc::fence_proxy_async(); sctc::tc_fence_before(); __syncthreads(); sctc::tc_fence_after(); };
     // wait until every MMA issued so far (layer GEMMs and weight gradients) has completed
     auto drain_mma = [&]() {
-        if (tid == 0) sctc::umma_commit(T.mma_done);
+        T.commit();
         mbar_wait(T.mma_done, T.mma_phase); T.mma_phase ^= 1; sctc::tc_fence_after();
     };
 
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 plane_to_act(T, st + (TS_R + 1) * kStashPlane, T.Z(), h);      // r1 -> Z (h keeps this thread's r1 values)
                 T.gemm(TM_ACC0, T.Y(), false);                                   // V2T : r1_bar = V2^T o2_bar
                 T.commit();                                                      // the epilogue overlaps the weight-gradient MMAs
-                if (tid == 0) wgrad(WG_V2, T.Y(), T.Z());
+                if (w0) wgrad(WG_V2, T.Y(), T.Z());
                 T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) v[i] = h[i] > 0.f ? v[i] : 0.f;
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 plane_to_act(T, st + (TS_R + 0) * kStashPlane, T.U(), h);      // r0 -> U
                 T.gemm(TM_ACC0, T.X(), false);                                   // V1T
                 T.commit();
-                if (tid == 0) wgrad(WG_V1, T.X(), T.U());
+                if (w0) wgrad(WG_V1, T.X(), T.U());
                 T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) v[i] = h[i] > 0.f ? v[i] : 0.f;
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 T.gemm(TM_ACC0, T.Z(), false);                                   // V0FT -> feat_bar
                 T.gemm(TM_ACC1, T.Z(), false);                                   // V0PT -> pe_bar (rgb)
                 T.commit();
-                if (tid == 0) { wgrad(WG_V0F, T.Z(), T.Y()); wgrad(WG_V0P, T.Z(), T.P()); }
+                if (w0) { wgrad(WG_V0F, T.Z(), T.Y()); wgrad(WG_V0P, T.Z(), T.P()); }
                 T.wait_and_load(TM_ACC0, v);
                 st_store(sc + TS_FB * kStashPlane, r, ch, v);
                 colsum_shared(vacc + VA_B5F, v, ch, lane);
@@ -304,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                     st_store(sc + (TS_SB + l) * kStashPlane, r, ch, w2);
                     row_store(qcur, r, ch, v); row_store(T.Z(), r, ch, h);
                     publish();
-                    if (tid == 0) {
+                    if (w0) {
                         if (l < 3) wgrad(l == 0 ? WG_A0 : (l == 1 ? WG_A1 : WG_A2), T.Z(), T.X());
                         if (l == 1) wgrad(WG_B1, T.Z(), qprev);
                         if (l == 2) wgrad(WG_B2, T.Z(), qprev);
@@ -329,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 colsum_shared(vacc + VA_W5, w1, ch, lane);
                 row_store(T.Z(), r, ch, h);
                 publish();
-                if (tid == 0) wgrad(WG_W4, T.Z(), T.U());
+                if (w0) wgrad(WG_W4, T.Z(), T.U());
             }
 
             // ================================================================================ first-order sweep
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
             if (MODE == 0) {
                 row_store(T.Z(), r, ch, h);                                      // h4 -> Z  (Z = g4: weight gradient W4 retired above)
                 publish();
-                if (tid == 0) wgrad(WG_W5F, T.X(), T.Z());
+                if (w0) wgrad(WG_W5F, T.X(), T.Z());
             }
             // layers 3..0: dW_{l+1} += a_{l+1}_bar (x) h_l ; a_l_bar = (W_{l+1}^T a_{l+1}_bar) s_l + SB_l t_l
             //   a_bar alternates Y -> X -> Y -> X -> Y ; h_l is loaded into U / Z alternately
@@ -378,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 if (l < 2) { T.gemm(TM_ACC1, acur, false); }                     // A2T | A1T  -> pe_bar
                 T.gemm(TM_ACC0, acur, false);                                    // W4T | W3T | B2T | B1T
                 T.commit();
-                if (tid == 0) {
+                if (w0) {
                     wgrad(l == 3 ? WG_W4 : (l == 2 ? WG_W3 : (l == 1 ? WG_B2 : WG_B1)), acur, hbuf);
                     if (l < 2) wgrad(l == 1 ? WG_A2 : WG_A1, acur, T.P());
                 }
@@ -400,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
             }
             // a0_bar is in Y: dA0 += a0_bar (x) pe ; pe_bar += A0^T a0_bar
             T.gemm(TM_ACC1, T.Y(), false);                                       // A0T
-            if (tid == 0) wgrad(WG_A0, T.Y(), T.P());
+            if (w0) wgrad(WG_A0, T.Y(), T.P());
             T.finish_and_load(TM_ACC1, w1);
             fold_pe_tc(T, w1);
             __syncthreads();

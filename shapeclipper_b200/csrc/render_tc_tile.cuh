@@ -15,6 +15,7 @@ struct TileTC {
     uint32_t mma_phase;
     uint32_t tmem;
     int tid, lane, warp, row, ch;
+    bool w0;                    // member of the issuing warp (warp 0, warp-uniform)
     int b, first, S, rays_per_tile;
     float beta;
 #ifdef SC_TC_TRACE
@@ -32,7 +33,7 @@ struct TileTC {
 
     // thread 0: commit the phase's layer GEMMs. MMAs issued AFTER this (weight gradients) are covered by the NEXT phase's
     // commit: their operand buffers must stay untouched until the next wait_and_load() has returned.
-    __device__ __forceinline__ void commit() { if (tid == 0) sctc::umma_commit(mma_done); }
+    __device__ __forceinline__ void commit() { if (w0) umma_commit_elect(mma_done); }
     __device__ __forceinline__ void finish_and_load(uint32_t acc_col, float (&v)[NC]) { commit(); wait_and_load(acc_col, v); }
     // everyone: wait for the accumulator, then read this thread's NC columns
     __device__ __forceinline__ void wait_and_load(uint32_t acc_col, float (&v)[NC]) {
@@ -49,7 +50,7 @@ struct TileTC {
         mark();
         const uint8_t* w = wr.acquire();
         mark();
-        if (tid == 0) { issue_layer_gemm(tmem + acc_col, a, w, accumulate); wr.release(); }
+        if (w0) { issue_layer_gemm(tmem + acc_col, a, w, accumulate); wr.release(); }
     }
 };
 
