@@ -80,13 +80,9 @@ __device__ __forceinline__ void plane_to_act(const TileTC& T, const float* plane
 }
 // pe_bar (this thread's 16 columns of row r) folded into x~_bar: XTB[k % 3][r] += pe_bar_k * d pe_k / d x~
 __device__ __forceinline__ void fold_pe_tc(const TileTC& T, const float (&v)[NC]) {
-    float g[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < NC; ++i) {
-        const int k = NC * T.ch + i;
-        if (k < NPE) g[k % 3] = fmaf(v[i], dpe_tc(T.P(), k, T.row), g[k % 3]);
-    }
     if (NC * T.ch < NPE) {
+        float g[3] = {0.f, 0.f, 0.f};
+        pe_fold(T.P(), T.row, T.ch, v, g);
         atomicAdd(T.pv(PV_XTB0) + T.row, g[0]); atomicAdd(T.pv(PV_XTB1) + T.row, g[1]); atomicAdd(T.pv(PV_XTB2) + T.row, g[2]);
     }
 }
@@ -181,6 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
             tc_tile_setup<MODE>(T, a);
             if (use_saved) {
                 st = reinterpret_cast<float*>(a.saved) + (size_t)tile * TS_SAVED_PLANES * kStashPlane;
+                if (MODE == 0) st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);      // r2, consumed after the ray phase: HBM latency hidden
                 saved_vectors<false>(T, st + TS_SAVED_PV * kStashPlane);
                 __syncthreads();
             } else {
@@ -215,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 }
                 __syncthreads();
                 // o2_bar = (V3^T o3_bar) * [r2 > 0] -> Y ; dV3 += o3_bar (x) r2
-                st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);
+                if (!use_saved) st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);
                 {
                     const float o0 = T.pv(PV_CB0)[r], o1 = T.pv(PV_CB1)[r], o2 = T.pv(PV_CB2)[r];
 #pragma unroll
@@ -268,14 +265,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 {
                     const float gb[3] = {T.pv(PV_GXB0)[r] * T.pv(PV_SGN)[r], T.pv(PV_GXB1)[r], T.pv(PV_GXB2)[r]};
                     float curv[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int i = 0; i < NC; ++i) {
-                        const int k = c0 + i;
-                        if (k < NPE) {
-                            v[i] = gb[k % 3] * dpe_tc(T.P(), k, r);
-                            curv[k % 3] = fmaf(d2pe_tc(T.P(), k, r), h[i], curv[k % 3]);
-                        } else v[i] = 0.f;
-                    }
+                    pe_second(T.P(), r, ch, gb, h, v, curv);
                     if (c0 < NPE) {
                         atomicAdd(T.pv(PV_XTB0) + r, gb[0] * curv[0]); atomicAdd(T.pv(PV_XTB1) + r, gb[1] * curv[1]);
                         atomicAdd(T.pv(PV_XTB2) + r, gb[2] * curv[2]);

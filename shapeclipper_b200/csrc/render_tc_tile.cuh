@@ -87,6 +87,96 @@ __device__ __forceinline__ float d2pe_tc(const uint8_t* P, int k, int p) {
     return -fr * fr * act_elem(P, p, k);
 }
 
+// ---- posenc derivatives of one row for the 16 columns of column group CH, with compile-time column roles.
+// d pe_k / d x~ = +-2^f pe_partner(k) (sin <-> cos, 3 columns away), d2 pe_k / d x~2 = -4^f pe_k. The row's posenc values are read
+// back from the operand plane with four 16-byte loads per plane (columns 16 CH - 8 .. 16 CH + 23, conflict-free) instead of
+// one 2-byte gather per element with run-time (k - 3) / 6 arithmetic (ncu: 30 % of the backward kernel's instructions).
+template <int CH>
+__device__ __forceinline__ void pe_row_values(const uint8_t* P, int r, float (&val)[32]) {
+    const uint8_t* hi = P + r * 128;
+    const uint8_t* lo = hi + kPlaneBytes;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int chunk = 2 * CH - 1 + c;                          // 8 columns each
+        if (chunk < 0 || chunk > 4) {                              // columns >= 40 are zero padding
+#pragma unroll
+            for (int j = 0; j < 8; ++j) val[8 * c + j] = 0.f;
+            continue;
+        }
+        const int pos = (chunk ^ (r & 7)) << 4;
+        const uint4 h = *reinterpret_cast<const uint4*>(hi + pos);
+        const uint4 l = *reinterpret_cast<const uint4*>(lo + pos);
+        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
+        const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 a = __bfloat1622float2(hp[e]), b = __bfloat1622float2(lp[e]);
+            val[8 * c + 2 * e] = a.x + b.x; val[8 * c + 2 * e + 1] = a.y + b.y;
+        }
+    }
+}
+// d1[i] = d pe_k / d x~, d2[i] = d2 pe_k / d x~2 for k = 16 CH + i (0 beyond the 39 posenc columns)
+template <int CH>
+__device__ __forceinline__ void pe_derivs(const uint8_t* P, int r, float (&d1)[NC], float (&d2)[NC]) {
+    float val[32];
+    pe_row_values<CH>(P, r, val);
+    constexpr int base = 8 * (2 * CH - 1);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int k = NC * CH + i;
+        if (k >= NPE) { d1[i] = 0.f; d2[i] = 0.f; }
+        else if (k < 3) { d1[i] = 1.f; d2[i] = 0.f; }
+        else {
+            const int f = (k - 3) / 6, rr = (k - 3) % 6;
+            const float fr = (float)(1 << f);
+            d1[i] = (rr < 3) ? fr * val[k + 3 - base] : -fr * val[k - 3 - base];
+            d2[i] = -fr * fr * val[k - base];
+        }
+    }
+}
+// g[c] += sum over this thread's columns k with k % 3 == c of v[i] * d pe_k / d x~
+template <int CH>
+__device__ __forceinline__ void pe_fold_ch(const uint8_t* P, int r, const float (&v)[NC], float (&g)[3]) {
+    float d1[NC], d2[NC];
+    pe_derivs<CH>(P, r, d1, d2);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int k = NC * CH + i;
+        if (k < NPE) g[k % 3] = fmaf(v[i], d1[i], g[k % 3]);
+    }
+}
+__device__ __forceinline__ void pe_fold(const uint8_t* P, int r, int ch, const float (&v)[NC], float (&g)[3]) {
+    switch (ch) {                                    // ch = warp >> 2: warp-uniform
+        case 0: pe_fold_ch<0>(P, r, v, g); break;
+        case 1: pe_fold_ch<1>(P, r, v, g); break;
+        case 2: pe_fold_ch<2>(P, r, v, g); break;
+        default: break;                              // columns 48..63: no posenc feature
+    }
+}
+// second-order prologue: v[i] = gb[k % 3] * d pe_k ; curv[c] += d2 pe_k * h[i]
+template <int CH>
+__device__ __forceinline__ void pe_second_ch(const uint8_t* P, int r, const float (&gb)[3], const float (&h)[NC], float (&v)[NC], float (&curv)[3]) {
+    float d1[NC], d2[NC];
+    pe_derivs<CH>(P, r, d1, d2);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const int k = NC * CH + i;
+        if (k < NPE) { v[i] = gb[k % 3] * d1[i]; curv[k % 3] = fmaf(d2[i], h[i], curv[k % 3]); }
+        else v[i] = 0.f;
+    }
+}
+__device__ __forceinline__ void pe_second(const uint8_t* P, int r, int ch, const float (&gb)[3], const float (&h)[NC], float (&v)[NC], float (&curv)[3]) {
+    switch (ch) {
+        case 0: pe_second_ch<0>(P, r, gb, h, v, curv); break;
+        case 1: pe_second_ch<1>(P, r, gb, h, v, curv); break;
+        case 2: pe_second_ch<2>(P, r, gb, h, v, curv); break;
+        default:
+#pragma unroll
+            for (int i = 0; i < NC; ++i) v[i] = 0.f;
+            break;
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void tc_tile_setup(const TileTC& T, const ScRenderArgs& a)
 {
@@ -271,11 +361,7 @@ __device__ __forceinline__ void tc_tile_forward(TileTC& T, const ScRenderArgs& a
     if (STASH_ALL) st_store(st + TS_GPE * kStashPlane, r, ch, v);
     {   // gx~_c = sum_k gpe_k dpe_k : per-thread partial over this thread's columns
         float g[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int i = 0; i < NC; ++i) {
-            const int k = c0 + i;
-            if (k < NPE) g[k % 3] = fmaf(v[i], dpe_tc(T.P(), k, r), g[k % 3]);
-        }
+        pe_fold(T.P(), r, ch, v, g);
         T.pv(PX_A + ch)[r] = g[0]; T.pv(PX_B + ch)[r] = g[1]; T.pv(PX_C + ch)[r] = g[2];
     }
     __syncthreads();
