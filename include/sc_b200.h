@@ -142,6 +142,13 @@ int sc_render_grad_finalize(const float* grad_partial, int n_ctas, const float* 
                             float* const* out_b, float* z_sdf_bar, float* z_rgb_bar, float* beta_bar,
                             cudaStream_t stream);
 
+/* Same, but out_w / out_b are ADDED to (fused gradient accumulation into existing .grad tensors: one launch instead of one
+ * accumulation kernel per parameter); z_sdf_bar / z_rgb_bar / beta_bar are still overwritten. */
+int sc_render_grad_finalize_accumulate(const float* grad_partial, int n_ctas, const float* cb_bar, const float* z_sdf,
+                                       const float* z_rgb, const float* blob, int batch, float* const* out_w,
+                                       float* const* out_b, float* z_sdf_bar, float* z_rgb_bar, float* beta_bar,
+                                       cudaStream_t stream);
+
 /* ---- CLIP ViT image tower + cosine k-NN ------------------------------------------
  * Replaces clip_model.encode_image + F.normalize (CLIP_anno.py:166-167; openai/CLIP, un-vendored dependency) and
  * NN_annotator.calc_matches (CLIP_anno.py:29-57). GEMMs run on tcgen05 tensor cores from TMA-staged bf16 tiles with

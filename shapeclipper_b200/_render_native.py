@@ -63,6 +63,8 @@ def declare(L):
         L.sc_render_backward.restype = i
         L.sc_render_grad_finalize.argtypes = [vp, i, vp, vp, vp, vp, i, vp, vp, vp, vp, vp, vp]
         L.sc_render_grad_finalize.restype = i
+        L.sc_render_grad_finalize_accumulate.argtypes = L.sc_render_grad_finalize.argtypes
+        L.sc_render_grad_finalize_accumulate.restype = i
 
 
 def _p(t):

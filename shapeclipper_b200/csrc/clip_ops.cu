@@ -110,9 +110,14 @@ __global__ void attention_kernel(const float* __restrict__ qkv, int T, int W, bf
         __syncwarp();
         float mx = -INFINITY;
         for (int tk = lane; tk < T; tk += 32) {
-            float s = 0.f;
-#pragma unroll 16
-            for (int d = 0; d < 64; ++d) s = fmaf(Qw[d], Ks[tk * 65 + d], s);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;                 // four independent chains: the dot is latency-bound
+            const float* kr = Ks + tk * 65;
+#pragma unroll
+            for (int d = 0; d < 64; d += 4) {
+                s0 = fmaf(Qw[d], kr[d], s0); s1 = fmaf(Qw[d + 1], kr[d + 1], s1);
+                s2 = fmaf(Qw[d + 2], kr[d + 2], s2); s3 = fmaf(Qw[d + 3], kr[d + 3], s3);
+            }
+            const float s = (s0 + s1) + (s2 + s3);
             P[tk] = s; mx = fmaxf(mx, s);
         }
         mx = warp_max(mx);
@@ -120,12 +125,17 @@ __global__ void attention_kernel(const float* __restrict__ qkv, int T, int W, bf
         for (int tk = lane; tk < T; tk += 32) { const float e = __expf(P[tk] - mx); P[tk] = e; sum += e; }
         sum = warp_sum(sum);
         __syncwarp();
-        float o0 = 0.f, o1 = 0.f;
-        for (int tk = 0; tk < T; ++tk) {
-            const float p = P[tk];
+        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+        int tk = 0;
+        for (; tk + 1 < T; tk += 2) {
+            const float p = P[tk], q = P[tk + 1];
             o0 = fmaf(p, Vs[tk * 65 + lane], o0);
             o1 = fmaf(p, Vs[tk * 65 + 32 + lane], o1);
+            o2 = fmaf(q, Vs[(tk + 1) * 65 + lane], o2);
+            o3 = fmaf(q, Vs[(tk + 1) * 65 + 32 + lane], o3);
         }
+        if (tk < T) { const float p = P[tk]; o0 = fmaf(p, Vs[tk * 65 + lane], o0); o1 = fmaf(p, Vs[tk * 65 + 32 + lane], o1); }
+        o0 += o2; o1 += o3;
         const float inv = 1.f / sum;
         const size_t o = ((size_t)b * T + tq) * W + h * 64;
         split_store(hi, lo, o + lane, o0 * inv);

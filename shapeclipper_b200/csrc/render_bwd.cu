@@ -596,7 +596,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_bwd_kernel(const ScRenderA
 
 // ---------------------------------------------------------------------------------------------------------
 // Finalisation: per-CTA partials + per-image bias adjoints -> nn.Linear-layout gradients, latent and beta grads.
-struct FinalizeOut { float* w[10]; float* b[10]; float* z_sdf_bar; float* z_rgb_bar; float* beta_bar; };
+struct FinalizeOut { float* w[10]; float* b[10]; float* z_sdf_bar; float* z_rgb_bar; float* beta_bar;     int accumulate;
+};
 
 __device__ __forceinline__ float psum(const float* __restrict__ partial, int n, int idx) {
     float s = 0.f;
@@ -631,11 +632,13 @@ __global__ void finalize_kernel(const float* __restrict__ partial, int n, const 
                                 const float* __restrict__ blob, int B, FinalizeOut out)
 {
     const float r2 = 0.70710678118654752440f;
+    // parameter gradients: overwrite, or add to what is there (fused gradient accumulation into p.grad)
+    auto put = [&](float* p, float v) { *p = out.accumulate ? *p + v : v; };
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < F_W1) {                                               // sdf lin0.weight [64][103]
         if (!out.w[0]) return;
         const int o = idx / 103, c = idx % 103;
-        out.w[0][idx] = c < 39 ? psum(partial, n, G_A0 + o * 39 + c) : cb_outer(cbb, z_sdf, B, CB_C0, CB_C0D, o, c - 39);
+        put(&out.w[0][idx], c < 39 ? psum(partial, n, G_A0 + o * 39 + c) : cb_outer(cbb, z_sdf, B, CB_C0, CB_C0D, o, c - 39));
     } else if (idx < F_W3) {                                        // sdf lin1 / lin2 .weight [64][167]
         const int l = idx < F_W2 ? 1 : 2;
         if (!out.w[l]) return;
@@ -645,16 +648,16 @@ __global__ void finalize_kernel(const float* __restrict__ partial, int n, const 
         if (c < 64) v = psum(partial, n, gB + o * 64 + c);
         else if (c < 103) v = psum(partial, n, gA + o * 39 + (c - 64));
         else v = cb_outer(cbb, z_sdf, B, CB_C0 + l, CB_C0D + l, o, c - 103);
-        out.w[l][e] = r2 * v;
+        put(&out.w[l][e], r2 * v);
     } else if (idx < F_W5) {                                        // lin3 / lin4
         const int l = idx < F_W4 ? 3 : 4;
         if (!out.w[l]) return;
         const int e = idx - (l == 3 ? F_W3 : F_W4);
-        out.w[l][e] = psum(partial, n, (l == 3 ? G_W3 : G_W4) + e);
+        put(&out.w[l][e], psum(partial, n, (l == 3 ? G_W3 : G_W4) + e));
     } else if (idx < F_V0) {                                        // lin5.weight [65][64]
         if (!out.w[5]) return;
         const int e = idx - F_W5, o = e / 64, k = e % 64;
-        out.w[5][e] = o == 0 ? psum(partial, n, G_W5 + k) : psum(partial, n, G_W5F + (o - 1) * 64 + k);
+        put(&out.w[5][e], o == 0 ? psum(partial, n, G_W5 + k) : psum(partial, n, G_W5F + (o - 1) * 64 + k));
     } else if (idx < F_V1) {                                        // rgb lin0.weight [64][167]
         if (!out.w[6]) return;
         const int e = idx - F_V0, o = e / 167, c = e % 167;
@@ -662,33 +665,33 @@ __global__ void finalize_kernel(const float* __restrict__ partial, int n, const 
         if (c < 39) v = psum(partial, n, G_V0P + o * 39 + c);
         else if (c < 103) v = cb_outer(cbb, z_rgb, B, CB_RGB, -1, o, c - 39);
         else v = psum(partial, n, G_V0F + o * 64 + (c - 103));
-        out.w[6][e] = v;
+        put(&out.w[6][e], v);
     } else if (idx < F_V3) {
         const int l = idx < F_V2 ? 7 : 8;
         if (!out.w[l]) return;
         const int e = idx - (l == 7 ? F_V1 : F_V2);
-        out.w[l][e] = psum(partial, n, (l == 7 ? G_V1 : G_V2) + e);
+        put(&out.w[l][e], psum(partial, n, (l == 7 ? G_V1 : G_V2) + e));
     } else if (idx < F_BIAS) {
         if (!out.w[9]) return;
         const int e = idx - F_V3;
-        out.w[9][e] = psum(partial, n, G_V3 + e);
+        put(&out.w[9][e], psum(partial, n, G_V3 + e));
     } else if (idx < F_BIAS_END) {
         int e = idx - F_BIAS;
         if (e < 192) {                                              // sdf lin0..2 bias
             const int l = e / 64, o = e % 64;
-            if (out.b[l]) out.b[l][o] = cb_sum(cbb, B, CB_C0 + l, CB_C0D + l, o);
+            if (out.b[l]) put(&out.b[l][o], cb_sum(cbb, B, CB_C0 + l, CB_C0D + l, o));
             return;
         }
         e -= 192;
-        if (e < 128) { const int l = 3 + e / 64, o = e % 64; if (out.b[l]) out.b[l][o] = psum(partial, n, (l == 3 ? G_B3 : G_B4) + o); return; }
+        if (e < 128) { const int l = 3 + e / 64, o = e % 64; if (out.b[l]) put(&out.b[l][o], psum(partial, n, (l == 3 ? G_B3 : G_B4) + o)); return; }
         e -= 128;
-        if (e < 65) { if (out.b[5]) out.b[5][e] = e == 0 ? psum(partial, n, G_B5) : psum(partial, n, G_B5F + e - 1); return; }
+        if (e < 65) { if (out.b[5]) put(&out.b[5][e], e == 0 ? psum(partial, n, G_B5) : psum(partial, n, G_B5F + e - 1)); return; }
         e -= 65;
-        if (e < 64) { if (out.b[6]) out.b[6][e] = cb_sum(cbb, B, CB_RGB, -1, e); return; }
+        if (e < 64) { if (out.b[6]) put(&out.b[6][e], cb_sum(cbb, B, CB_RGB, -1, e)); return; }
         e -= 64;
-        if (e < 128) { const int l = 7 + e / 64, o = e % 64; if (out.b[l]) out.b[l][o] = psum(partial, n, (l == 7 ? G_C1R : G_C2R) + o); return; }
+        if (e < 128) { const int l = 7 + e / 64, o = e % 64; if (out.b[l]) put(&out.b[l][o], psum(partial, n, (l == 7 ? G_C1R : G_C2R) + o)); return; }
         e -= 128;
-        if (out.b[9]) out.b[9][e] = psum(partial, n, G_C3R + e);
+        if (out.b[9]) put(&out.b[9][e], psum(partial, n, G_C3R + e));
     } else {
         idx -= F_END;
         const float* lat = blob + kLatentOffset;
@@ -748,15 +751,32 @@ extern "C" int sc_render_backward(const ScRenderArgs* a, cudaStream_t stream)
     return (int)cudaGetLastError();
 }
 
-extern "C" int sc_render_grad_finalize(const float* grad_partial, int n_ctas, const float* cb_bar, const float* z_sdf,
-                                       const float* z_rgb, const float* blob, int batch, float* const* out_w,
-                                       float* const* out_b, float* z_sdf_bar, float* z_rgb_bar, float* beta_bar,
-                                       cudaStream_t stream)
+static int finalize_impl(const float* grad_partial, int n_ctas, const float* cb_bar, const float* z_sdf,
+                         const float* z_rgb, const float* blob, int batch, float* const* out_w,
+                         float* const* out_b, float* z_sdf_bar, float* z_rgb_bar, float* beta_bar, int accumulate,
+                         cudaStream_t stream)
 {
     FinalizeOut o;
+    o.accumulate = accumulate;
     for (int i = 0; i < 10; ++i) { o.w[i] = out_w[i]; o.b[i] = out_b[i]; }
     o.z_sdf_bar = z_sdf_bar; o.z_rgb_bar = (z_rgb != nullptr) ? z_rgb_bar : nullptr; o.beta_bar = beta_bar;
     const int total = F_END + 2 * batch * 64 + 1;
     finalize_kernel<<<(total + 127) / 128, 128, 0, stream>>>(grad_partial, n_ctas, cb_bar, z_sdf, z_rgb, blob, batch, o);
     return (int)cudaGetLastError();
+}
+
+extern "C" int sc_render_grad_finalize(const float* grad_partial, int n_ctas, const float* cb_bar, const float* z_sdf,
+                                       const float* z_rgb, const float* blob, int batch, float* const* out_w,
+                                       float* const* out_b, float* z_sdf_bar, float* z_rgb_bar, float* beta_bar,
+                                       cudaStream_t stream)
+{
+    return finalize_impl(grad_partial, n_ctas, cb_bar, z_sdf, z_rgb, blob, batch, out_w, out_b, z_sdf_bar, z_rgb_bar, beta_bar, 0, stream);
+}
+
+extern "C" int sc_render_grad_finalize_accumulate(const float* grad_partial, int n_ctas, const float* cb_bar, const float* z_sdf,
+                                                  const float* z_rgb, const float* blob, int batch, float* const* out_w,
+                                                  float* const* out_b, float* z_sdf_bar, float* z_rgb_bar, float* beta_bar,
+                                                  cudaStream_t stream)
+{
+    return finalize_impl(grad_partial, n_ctas, cb_bar, z_sdf, z_rgb, blob, batch, out_w, out_b, z_sdf_bar, z_rgb_bar, beta_bar, 1, stream);
 }

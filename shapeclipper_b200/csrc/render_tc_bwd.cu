@@ -174,12 +174,15 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
             T.first = (tile % tiles_per_image) * per_tile;
             float* cbb = a.cb_bar + (size_t)T.b * kCbRows * 64;
             __syncthreads();
+            T.mark();                                                            // [trace] tile start
             tc_tile_setup<MODE>(T, a);
+            T.mark();                                                            // [trace] setup done
             if (use_saved) {
                 st = reinterpret_cast<float*>(a.saved) + (size_t)tile * TS_SAVED_PLANES * kStashPlane;
                 if (MODE == 0) st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);      // r2, consumed after the ray phase: HBM latency hidden
                 saved_vectors<false>(T, st + TS_SAVED_PV * kStashPlane);
                 __syncthreads();
+                T.mark();                                                        // [trace] saved vectors loaded
             } else {
                 tc_tile_forward<MODE, true>(T, a, second, MODE == 0);
             }
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 __syncthreads();
             } else {
                 ray_phase_backward(T, a, vacc + VA_BETA, kThreads);
+                T.mark();                                                        // [trace] ray phase done
 
                 // ============================================================================ RGB backward
                 if (tid < M_TILE) {                                  // o3_bar = colour_bar * col (1 - col)

@@ -177,6 +177,39 @@ __device__ __forceinline__ void pe_second(const uint8_t* P, int r, int ch, const
     }
 }
 
+// posenc columns 16 CH .. 16 CH + 15 of one point: [x, sin(2^f x), cos(2^f x)]_{f = 0..5}, 39 features then zero padding.
+// Accurate sincosf at 2^0 and 2^3, angle doubling (sin 2a = 2 s c, cos 2a = 1 - 2 s^2) for the two octaves after each anchor:
+// error growth 4x at most (~2.5e-7), well below the hi/lo-bf16 operand rounding of this path. Octaves a column group does
+// not hold are never evaluated.
+__host__ __device__ constexpr bool pe_oct_needed(int f, int c, int k0, int k1) {      // does [k0, k1) hold sin or cos of (octave f, coord c)?
+    return (3 + 6 * f + c >= k0 && 3 + 6 * f + c < k1) || (6 + 6 * f + c >= k0 && 6 + 6 * f + c < k1);
+}
+__host__ __device__ constexpr int pe_last_needed(int anchor, int c, int k0, int k1) {  // last needed octave of {anchor .. anchor + 2}, or -1
+    return pe_oct_needed(anchor + 2, c, k0, k1) ? anchor + 2 : (pe_oct_needed(anchor + 1, c, k0, k1) ? anchor + 1 :
+           (pe_oct_needed(anchor, c, k0, k1) ? anchor : -1));
+}
+template <int CH>
+__device__ __forceinline__ void posenc_cols(const float (&xt)[3], float (&v)[NC]) {
+    constexpr int k0 = NC * CH, k1 = k0 + NC;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) v[i] = (k0 + i < 3) ? xt[(k0 + i) % 3] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float sn = 0.f, cs = 1.f;
+#pragma unroll
+        for (int f = 0; f < 6; ++f) {
+            const int anchor = (f < 3) ? 0 : 3;
+            if (f > pe_last_needed(anchor, c, k0, k1)) continue;       // compile-time after unrolling
+            if (f == 0) sincosf(xt[c], &sn, &cs);
+            else if (f == 3) sincosf(xt[c] * 8.f, &sn, &cs);
+            else { const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn; sn = s2; cs = c2; }
+            const int ks = 3 + 6 * f + c, kc = ks + 3;
+            if (ks >= k0 && ks < k1) v[ks - k0] = sn;
+            if (kc >= k0 && kc < k1) v[kc - k0] = cs;
+        }
+    }
+}
+
 template <int MODE>
 __device__ __forceinline__ void tc_tile_setup(const TileTC& T, const ScRenderArgs& a)
 {
@@ -225,24 +258,15 @@ __device__ __forceinline__ void tc_tile_setup(const TileTC& T, const ScRenderArg
         T.pv(scr::PV_X0)[p] = x0; T.pv(scr::PV_X1)[p] = x1; T.pv(scr::PV_X2)[p] = x2;
     }
     const float xt[3] = {fabsf(x0), x1, x2};
-    // posenc: accurate sincosf at 2^0 and 2^3, angle doubling (sin 2a = 2 s c, cos 2a = 1 - 2 s^2) for the two octaves after
-    // each anchor: error growth 4x at most (~2.5e-7), well below the hi/lo-bf16 operand rounding of this path.
     float v[NC];
-    const int k0 = NC * T.ch;
+    switch (T.ch) {                                   // warp-uniform: column roles are compile-time inside each case
+        case 0: posenc_cols<0>(xt, v); break;
+        case 1: posenc_cols<1>(xt, v); break;
+        case 2: posenc_cols<2>(xt, v); break;
+        default:
 #pragma unroll
-    for (int i = 0; i < NC; ++i) v[i] = (k0 + i < 3) ? xt[(k0 + i) % 3] : 0.f;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float sn, cs;
-#pragma unroll
-        for (int f = 0; f < 6; ++f) {
-            if (f == 0) sincosf(xt[c], &sn, &cs);
-            else if (f == 3) sincosf(xt[c] * 8.f, &sn, &cs);
-            else { const float s2 = 2.f * sn * cs, c2 = 1.f - 2.f * sn * sn; sn = s2; cs = c2; }
-            const int ks = 3 + 6 * f + c - k0, kc = ks + 3;              // columns of sin / cos relative to this thread's group
-#pragma unroll
-            for (int i = 0; i < NC; ++i) { if (i == ks) v[i] = sn; if (i == kc) v[i] = cs; }
-        }
+            for (int i = 0; i < NC; ++i) v[i] = 0.f;  // columns 48..63: zero padding
+            break;
     }
     row_store(T.P(), p, T.ch, v);
     // per-tile bias tables: sdf layers 0..4 and rgb layers 0..2

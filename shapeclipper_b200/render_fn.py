@@ -66,21 +66,42 @@ def _new_args(**kw):
     return a
 
 
-def _finalize(L, partial, n_ctas, cb_bar, z_sdf, z_rgb, blob, B, ws, bs, need_rgb):
-    """-> (grads for weights[10], biases[10] (None where not produced), z_sdf_bar, z_rgb_bar, beta_eff_bar)."""
+# Fused gradient accumulation: the finalize kernel adds the parameter gradients straight into existing `.grad` tensors and
+# the autograd Function returns None for them — one launch instead of one accumulation kernel per parameter and call
+# (~70 launches per training step). OFF by default: it bypasses the parameters' AccumulateGrad nodes, so hooks on them
+# (e.g. the reference's DistributedDataParallel) would not fire. step.TrainStep, which owns the flat gradient buffer and its
+# all-reduce, switches it on around its forward/backward.
+FUSED_GRAD_ACCUMULATION = False
+
+
+def _finalize(L, partial, n_ctas, cb_bar, z_sdf, z_rgb, blob, B, ws, bs, need_rgb, needs=None):
+    """-> (grads for weights[10], biases[10] (None where not produced), z_sdf_bar, z_rgb_bar, beta_eff_bar).
+    needs: per-tensor needs_input_grad flags (weights then biases) of the calling Function, or None."""
     dev = blob.device
-    gw = [torch.empty_like(w) for w in ws[:_N_SDF]] + ([torch.empty_like(w) for w in ws[_N_SDF:]] if need_rgb else [None] * _N_RGB)
-    gb = [torch.empty_like(b) for b in bs[:_N_SDF]] + ([torch.empty_like(b) for b in bs[_N_SDF:]] if need_rgb else [None] * _N_RGB)
+    n_w = 10 if need_rgb else _N_SDF
+    live = list(ws[:n_w]) + list(bs[:n_w])
+    fused = FUSED_GRAD_ACCUMULATION and all(
+        (p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous() and p.grad.device == dev)
+        for p in live)
+    if fused:
+        gw = [w.grad for w in ws[:n_w]] + [None] * (10 - n_w)
+        gb = [b.grad for b in bs[:n_w]] + [None] * (10 - n_w)
+    else:
+        gw = [torch.empty_like(w) for w in ws[:n_w]] + [None] * (10 - n_w)
+        gb = [torch.empty_like(b) for b in bs[:n_w]] + [None] * (10 - n_w)
     warr = (ctypes.c_void_p * 10)(*[(g.data_ptr() if g is not None else None) for g in gw])
     barr = (ctypes.c_void_p * 10)(*[(g.data_ptr() if g is not None else None) for g in gb])
     z_sdf_bar = torch.empty(B, 64, device=dev)
     z_rgb_bar = torch.empty(B, 64, device=dev) if need_rgb else None
     beta_bar = torch.empty(1, device=dev)
+    fn = L.sc_render_grad_finalize_accumulate if fused else L.sc_render_grad_finalize
     with torch.cuda.device(dev):
-        _lib.check(L.sc_render_grad_finalize(rn._p(partial), n_ctas, rn._p(cb_bar), rn._p(z_sdf), rn._p(z_rgb), rn._p(blob), B,
-                                             warr, barr, rn._p(z_sdf_bar), rn._p(z_rgb_bar), rn._p(beta_bar),
-                                             _lib.stream_of(blob)), "sc_render_grad_finalize")
+        _lib.check(fn(rn._p(partial), n_ctas, rn._p(cb_bar), rn._p(z_sdf), rn._p(z_rgb), rn._p(blob), B,
+                      warr, barr, rn._p(z_sdf_bar), rn._p(z_rgb_bar), rn._p(beta_bar),
+                      _lib.stream_of(blob)), "sc_render_grad_finalize")
     rn.TIMERS.count()
+    if fused:                                     # already in p.grad: nothing for autograd to accumulate
+        gw, gb = [None] * 10, [None] * 10
     return gw, gb, z_sdf_bar, z_rgb_bar, beta_bar
 
 
@@ -145,9 +166,13 @@ class _RenderFn(torch.autograd.Function):
         rgb_bar, mask_bar, depth_bar, normal_bar = g(rgb_bar), g(mask_bar), g(depth_bar), g(normal_bar)
         n_ctas = L.sc_render_num_ctas()
         partial = torch.empty(n_ctas, L.sc_render_grad_floats(), device=dev)
-        cb_bar = torch.zeros(B, 7, 64, device=dev)
-        dirs_bar = torch.zeros(B, R, 3, device=dev); fac_bar = torch.zeros(B, R, device=dev)
-        loc_bar = torch.zeros(B, 3, device=dev); sd_bar = torch.zeros(B, device=dev)
+        zeros = torch.zeros(B * (7 * 64 + R * 4 + 4), device=dev)          # one fill for every atomically accumulated output
+        o = 0
+        cb_bar = zeros[o:o + B * 448].view(B, 7, 64); o += B * 448
+        dirs_bar = zeros[o:o + B * R * 3].view(B, R, 3); o += B * R * 3
+        fac_bar = zeros[o:o + B * R].view(B, R); o += B * R
+        loc_bar = zeros[o:o + B * 3].view(B, 3); o += B * 3
+        sd_bar = zeros[o:o + B]
         tc = _bwd_tc()
         scratch = rn.scratch(dev, backward=True, tc=tc)
         kblob = rn.packed_tc_blob(ws, bs, blob) if tc else blob

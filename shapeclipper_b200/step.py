@@ -15,6 +15,7 @@ Without them the step runs eagerly with identical results to calling the pieces 
 import torch
 
 from . import _render_native as rn
+from . import render_fn
 from .options import Options
 
 GRAD_LEAVES = ("pose", "intr", "scale_dist", "proj_latent_sdf", "proj_latent_rgb",
@@ -61,8 +62,13 @@ class TrainStep:
                 self.var[k].grad = None
         if self.side_work is not None:
             self.side_work()
-        _, loss = self.graph(self.opt, self.var, training=True, get_loss=True)
-        loss["all"].backward()
+        # parameter gradients go straight into the flat buffer's views (render_fn.FUSED_GRAD_ACCUMULATION)
+        old, render_fn.FUSED_GRAD_ACCUMULATION = render_fn.FUSED_GRAD_ACCUMULATION, True
+        try:
+            _, loss = self.graph(self.opt, self.var, training=True, get_loss=True)
+            loss["all"].backward()
+        finally:
+            render_fn.FUSED_GRAD_ACCUMULATION = old
         return loss
 
     def _capture(self, warmup):
