@@ -45,6 +45,17 @@ int sc_chamfer_backward(const float* xyz1, const float* xyz2, int batch, int n, 
                         const int32_t* idx1, const int32_t* idx2,
                         float* gradxyz1, float* gradxyz2, cudaStream_t stream);
 
+/* ---- ray geometry of the selected pixels --------------------------------------------
+ * Replaces utils/camera.py:157-196 (get_camera_grid, get_center_and_ray; perspective camera) + model/renderer.py:59-68.
+ * pose [B,3,4] world->camera, intr [B,3,3], ray_idx [B,R] int64 flat row-major pixel ids (NULL = pixels 0..R-1).
+ * -> cam_loc [B,3], unit ray_dirs [B,R,3], depth_fac [B,R]. backward: adjoints of those three (NULL = zero) ->
+ * pose_bar [B,3,4], intr_bar [B,3,3] (either may be NULL); workspace: batch * 18 floats. */
+int sc_pixel_rays_forward(const float* pose, const float* intr, const int64_t* ray_idx, int batch, int n_rays,
+                          int width, float* cam_loc, float* ray_dirs, float* depth_fac, cudaStream_t stream);
+int sc_pixel_rays_backward(const float* pose, const float* intr, const int64_t* ray_idx, int batch, int n_rays,
+                           int width, const float* cam_loc_bar, const float* ray_dirs_bar, const float* depth_fac_bar,
+                           float* workspace, float* pose_bar, float* intr_bar, cudaStream_t stream);
+
 /* ---- fused SDF/RGB-MLP volume renderer ----------------------------------
  * Replaces model/renderer.py:57-209 (Renderer.forward), model/implicit.py:138-239 (SDFNetwork.forward,
  * get_conditional_output, RGBNetwork.forward, LaplaceDensity) and the slice loop of utils/eval_3D.py:21-38.

@@ -44,6 +44,10 @@ def _declare(L):
     L.sc_chamfer_forward.restype = i
     L.sc_chamfer_backward.argtypes = [vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, vp]
     L.sc_chamfer_backward.restype = i
+    L.sc_pixel_rays_forward.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp]
+    L.sc_pixel_rays_forward.restype = i
+    L.sc_pixel_rays_backward.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, vp]
+    L.sc_pixel_rays_backward.restype = i
     from . import _render_native, clip
     _render_native.declare(L)
     clip.declare(L)

@@ -18,6 +18,58 @@ def inv3x3(m):
 
 
 def pixel_rays(pose, intr, H, W, ray_idx=None):
+    """Ray geometry of the selected pixels: CUDA tensors go through the fused kernels (one launch forward, two backward —
+    sc_pixel_rays_forward / _backward), anything else through the torch restatement below (same values to fp32 rounding)."""
+    if pose.is_cuda:
+        return _PixelRays.apply(pose, intr, ray_idx, int(H), int(W))
+    return pixel_rays_torch(pose, intr, H, W, ray_idx)
+
+
+class _PixelRays(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pose, intr, ray_idx, H, W):
+        from . import _lib, _render_native as rn
+        L = _lib.lib()
+        _lib.require_cuda(pose, intr, ray_idx)
+        B = pose.shape[0]
+        R = ray_idx.shape[1] if ray_idx is not None else H * W
+        p, k = rn._f32c(pose.detach()), rn._f32c(intr.detach())
+        idx = ray_idx.contiguous() if ray_idx is not None else None
+        if idx is not None and idx.dtype != torch.int64:
+            idx = idx.long()
+        dev = pose.device
+        center = torch.empty(B, 3, device=dev); dirs = torch.empty(B, R, 3, device=dev); fac = torch.empty(B, R, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.sc_pixel_rays_forward(_lib.ptr(p), _lib.ptr(k), _lib.ptr(idx), B, R, W, _lib.ptr(center), _lib.ptr(dirs),
+                                               _lib.ptr(fac), _lib.stream_of(p)), "sc_pixel_rays_forward")
+        rn.TIMERS.count()
+        ctx.save_for_backward(p, k, idx if idx is not None else p)
+        ctx.meta = (B, R, W, idx is not None)
+        ctx.set_materialize_grads(False)
+        return center, dirs, fac
+
+    @staticmethod
+    def backward(ctx, g_center, g_dirs, g_fac):
+        from . import _lib, _render_native as rn
+        L = _lib.lib()
+        p, k, idx = ctx.saved_tensors
+        B, R, W, has_idx = ctx.meta
+        dev = p.device
+        c = lambda t: rn._f32c(t) if t is not None else None
+        g_center, g_dirs, g_fac = c(g_center), c(g_dirs), c(g_fac)
+        need_pose, need_intr = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        pose_bar = torch.empty(B, 3, 4, device=dev) if need_pose else None
+        intr_bar = torch.empty(B, 3, 3, device=dev) if need_intr else None
+        ws = torch.empty(B * 18, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.sc_pixel_rays_backward(_lib.ptr(p), _lib.ptr(k), _lib.ptr(idx if has_idx else None), B, R, W,
+                                                _lib.ptr(g_center), _lib.ptr(g_dirs), _lib.ptr(g_fac), _lib.ptr(ws),
+                                                _lib.ptr(pose_bar), _lib.ptr(intr_bar), _lib.stream_of(p)), "sc_pixel_rays_backward")
+        rn.TIMERS.count(2)
+        return pose_bar, intr_bar, None, None, None
+
+
+def pixel_rays_torch(pose, intr, H, W, ray_idx=None):
     """pose [B,3,4] world->camera, intr [B,3,3]; ray_idx [B,R] int64 flat pixel ids (row-major) or None = all.
     -> cam_loc [B,3], unit ray_dirs [B,R,3], depth_fac [B,R] (ray length -> depth factor)."""
     B = pose.shape[0]

@@ -53,7 +53,13 @@ def _check_outputs(out, want, names, truth=None):
         if nm in ("rgb", "mask", "depth"):
             _close(got[nm], want[nm], nm)
         if nm == "normal":
-            _close(got[nm] * got["mask"], want[nm] * want["mask"], "normal*mask")
+            if truth is not None and truth.get("normal") is not None:      # ill-conditioned on cancelling rays: judge against fp64
+                t = truth["normal"].double().reshape(want[nm].shape) * truth["mask"].double().reshape(want["mask"].shape)
+                e_ref = float((want[nm].double() * want["mask"].double() - t).abs().max())
+                e_got = float((got[nm].detach().cpu().double() * got["mask"].detach().cpu().double() - t).abs().max())
+                assert e_got <= max(REL, 4 * e_ref), "normal*mask: err vs fp64 %.3e, reference fp32 err %.3e" % (e_got, e_ref)
+            else:
+                _close(got[nm] * got["mask"], want[nm] * want["mask"], "normal*mask")
         if truth is not None and truth.get(nm) is not None:
             t = truth[nm].double().reshape(want[nm].shape)
             scale = max(float(t.abs().max()), 1e-3)
@@ -157,11 +163,18 @@ def test_render_vs_oracle_default_size():
     sp = {k: v.detach() for k, v in sdf.state_dict().items() if k.startswith("lin")}
     rp = {k: v.detach() for k, v in rgb.state_dict().items()}
     torch.manual_seed(5)
-    want = R.render(sp, rp, ren.density.beta.detach(), pose, intr, sd, zs, zr, 224, 224, ray_idx=ridx, training=True)
+    draws = R.draw_render_rng(B * Rn, opt.render.n_samples_uniform, True)
+    want = R.render(sp, rp, ren.density.beta.detach(), pose, intr, sd, zs, zr, 224, 224, ray_idx=ridx, training=True, rng=draws)
+    # the same inputs and draws in fp64: the ray geometry of a 224-px image at focal 4 cancels (x - cx) / f to ~1e-3, so the
+    # fp32 reference itself carries ~1e-5 relative error in its ray directions; outputs that amplify it are judged against fp64
+    d64 = lambda t: t.double() if (t is not None and t.is_floating_point()) else t
+    truth = R.render({k: d64(v) for k, v in sp.items()}, {k: d64(v) for k, v in rp.items()}, d64(ren.density.beta.detach()),
+                     d64(pose), d64(intr), d64(sd), d64(zs), d64(zr), 224, 224, ray_idx=ridx, training=True,
+                     rng=tuple(d64(t) for t in draws))
     ren = ren.cuda()
     torch.manual_seed(5)
     got = ren(opt, pose.cuda(), intr.cuda(), sd.cuda(), zs.cuda(), zr.cuda(), ray_idx=ridx.cuda(), training=True)
-    _check_outputs(got, {k: want[k] for k in NAMES}, NAMES)
+    _check_outputs(got, {k: want[k] for k in NAMES}, NAMES, {k: truth[k] for k in NAMES})
 
 
 # ---------------------------------------------------------------------------------------------------- backward
@@ -257,3 +270,26 @@ def test_level_grid_matches_oracle():
     d1, d2, _, _ = eval_3D.chamfer_distance(opt, pts.reshape(2, -1, 3)[:, :500].contiguous(), pts.reshape(2, -1, 3)[:, 100:900].contiguous())
     f = eval_3D.compute_fscore(d1, d2)
     assert f.shape == (2, 6) and torch.isfinite(f).all()
+
+
+@pytest.mark.parametrize("use_idx", [True, False])
+def test_fused_pixel_rays_match_torch_restatement(use_idx):
+    """sc_pixel_rays_forward / _backward (utils/camera.py:157-196 + model/renderer.py:59-68) against the torch restatement
+    camera.pixel_rays_torch (itself pinned to the reference by the renderer golden tests): values and pose / intr gradients."""
+    from shapeclipper_b200 import camera, options, synthetic
+    opt = options.default_options(H=48, W=64)
+    opt.render.rand_sample = 300
+    b = synthetic.make_batch(opt, 3, seed=4, pin=False)
+    pose, intr = b["pose"].cuda(), b["intr"].cuda()
+    intr = intr + 0.01 * torch.randn_like(intr)                                # a general (not upper-triangular) K too
+    idx = b["ray_idx"].cuda() if use_idx else None
+    outs = []
+    for fn in (camera.pixel_rays, camera.pixel_rays_torch):
+        p, k = pose.clone().requires_grad_(True), intr.clone().requires_grad_(True)
+        c, d, f = fn(p, k, 48, 64, idx)
+        torch.manual_seed(0)
+        s = (c * torch.randn_like(c)).sum() + (d * torch.randn_like(d)).sum() + (f * torch.randn_like(f)).sum()
+        s.backward()
+        outs.append((c, d, f, p.grad, k.grad))
+    for name, a, w in zip(("center", "dirs", "depth_fac", "pose.grad", "intr.grad"), outs[0], outs[1]):
+        _close(a, w, name, 2e-5)
