@@ -56,6 +56,22 @@ int sc_pixel_rays_backward(const float* pose, const float* intr, const int64_t* 
                            int width, const float* cam_loc_bar, const float* ray_dirs_bar, const float* depth_fac_bar,
                            float* workspace, float* pose_bar, float* intr_bar, cudaStream_t stream);
 
+/* ---- render-consuming losses of one render: values and unit gradients -------------
+ * Replaces model/loss.py:19-97 as combined in model/graph.py:220-265: MSE(rgb), soft-IoU mask loss, trimmed normal loss,
+ * eikonal MSE. pass1 -> (caller: order = stable argsort(key)) -> pass2. rgb / normal [B,R,3], mask [B,R], eik [n_eik]
+ * (normal / eik may be NULL). workspace: sc_render_losses_workspace_floats(batch) floats. Outputs: losses[4] = render,
+ * mask, normal, eikonal and the gradient of each loss w.r.t. its inputs for unit upstream weight. */
+size_t sc_render_losses_workspace_floats(int batch);
+int sc_render_losses_pass1(const float* rgb, const float* rgb_t, const float* mask, const float* mask_t,
+                           const float* normal, const float* normal_t, const float* eik, int n_eik, int batch,
+                           int n_rays, float normal_l1, float* workspace, float* key, float* per_px,
+                           float* rgb_unit, float* normal_unit, float* normal_t_unit, float* eik_unit,
+                           cudaStream_t stream);
+int sc_render_losses_pass2(const float* mask, const float* mask_t, const float* normal, const float* normal_t,
+                           const int64_t* order, const float* per_px, int n_eik, int batch, int n_rays, float normal_l1,
+                           double normal_tol, float mask_mse, float* workspace, float* mask_unit, float* normal_unit,
+                           float* normal_t_unit, float* losses, cudaStream_t stream);
+
 /* ---- fused SDF/RGB-MLP volume renderer ----------------------------------
  * Replaces model/renderer.py:57-209 (Renderer.forward), model/implicit.py:138-239 (SDFNetwork.forward,
  * get_conditional_output, RGBNetwork.forward, LaplaceDensity) and the slice loop of utils/eval_3D.py:21-38.

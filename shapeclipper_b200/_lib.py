@@ -48,6 +48,13 @@ def _declare(L):
     L.sc_pixel_rays_forward.restype = i
     L.sc_pixel_rays_backward.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, vp]
     L.sc_pixel_rays_backward.restype = i
+    f, d = ctypes.c_float, ctypes.c_double
+    L.sc_render_losses_workspace_floats.argtypes = [i]
+    L.sc_render_losses_workspace_floats.restype = sz
+    L.sc_render_losses_pass1.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, f, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.sc_render_losses_pass1.restype = i
+    L.sc_render_losses_pass2.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, f, d, f, vp, vp, vp, vp, vp, vp]
+    L.sc_render_losses_pass2.restype = i
     from . import _render_native, clip
     _render_native.declare(L)
     clip.declare(L)

@@ -51,24 +51,38 @@ __device__ __forceinline__ void tile_weights_t(const TT& T, float& delta, float&
     T.pv(PV_W)[p] = w;
 }
 
+// upstream adjoints of ray r (8 floats: rgb(3) mask depth normal(3)); NULL pointers read as zero
+__device__ __forceinline__ void load_upstream(const ScRenderArgs& a, int b, int r, float (&ub)[8]) {
+    const bool valid = r < a.n_per_image;
+    const size_t g = (size_t)b * a.n_per_image + r;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        ub[c] = (valid && a.rgb_bar) ? a.rgb_bar[g * 3 + c] : 0.f;
+        ub[5 + c] = (valid && a.normal_bar) ? a.normal_bar[g * 3 + c] : 0.f;
+    }
+    ub[3] = (valid && a.mask_bar) ? a.mask_bar[g] : 0.f;
+    ub[4] = (valid && a.depth_bar) ? a.depth_bar[g] : 0.f;
+}
+
+// ub_pre: this thread's ray's upstream adjoints if the caller prefetched them (threads tid < rays_per_tile), else nullptr
 template <class TT>
-__device__ __forceinline__ void ray_phase_backward(TT& T, const ScRenderArgs& a, float* beta_acc, int nthreads)
+__device__ __forceinline__ void ray_phase_backward(TT& T, const ScRenderArgs& a, float* beta_acc, int nthreads,
+                                                   const float* ub_pre = nullptr)
 {
     const int tid = T.tid, lane = T.lane;
     float* part_beta = beta_acc;
                 for (int i = tid; i < 32 * 8; i += nthreads) T.ray[RAYX_ACC + i] = 0.f;
                 if (tid < T.rays_per_tile) {
-                    const int r = T.first + tid;
-                    const bool valid = r < a.n_per_image;
-                    const size_t g = (size_t)T.b * a.n_per_image + r;
                     float* ub = T.ray + RAYX_BAR + tid * 8;
+                    float u8[8];
+                    if (ub_pre != nullptr) {
     #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        ub[c] = (valid && a.rgb_bar) ? a.rgb_bar[g * 3 + c] : 0.f;
-                        ub[5 + c] = (valid && a.normal_bar) ? a.normal_bar[g * 3 + c] : 0.f;
+                        for (int c = 0; c < 8; ++c) u8[c] = ub_pre[c];
+                    } else {
+                        load_upstream(a, T.b, T.first + tid, u8);
                     }
-                    ub[3] = (valid && a.mask_bar) ? a.mask_bar[g] : 0.f;
-                    ub[4] = (valid && a.depth_bar) ? a.depth_bar[g] : 0.f;
+    #pragma unroll
+                    for (int c = 0; c < 8; ++c) ub[c] = u8[c];
                 }
                 __syncthreads();
                 float delta = 0.f, E = 0.f, Tr = 0.f, ea = 0.f, w = 0.f, wp = 0.f, z = 0.f, fac = 0.f;

@@ -61,6 +61,13 @@ constexpr int TS_H = 0, TS_Q = 5, TS_FEAT = 9, TS_R = 10, TS_GPE = 13, TS_FB = 1
 constexpr int TS_SAVED_PV = 14, TS_SAVED_PLANES = 15;
 constexpr int kSavedVecs = 13;
 // forward (store = true): per-point vectors the backward needs -> plane TS_SAVED_PV of the tile's saved block; backward: back.
+// backward, split in two so that the HBM latency of the loads overlaps the tile set-up: issue the loads into registers ...
+__device__ __forceinline__ void saved_vectors_prefetch(const TileTC& T, const float* plane, float (&reg)[13]) {
+    if (T.tid < M_TILE) {
+#pragma unroll
+        for (int i = 0; i < 13; ++i) reg[i] = __ldcg(plane + i * M_TILE + T.tid);
+    }
+}
 template <bool STORE>
 __device__ __forceinline__ void saved_vectors(const TileTC& T, float* plane) {
     constexpr int vecs[kSavedVecs] = {scr::PV_SDF, scr::PV_COL0, scr::PV_COL1, scr::PV_COL2, scr::PV_GX0, scr::PV_GX1, scr::PV_GX2,
@@ -71,6 +78,15 @@ __device__ __forceinline__ void saved_vectors(const TileTC& T, float* plane) {
             if (STORE) __stcg(plane + i * M_TILE + T.tid, T.pv(vecs[i])[T.tid]);
             else T.pv(vecs[i])[T.tid] = __ldcg(plane + i * M_TILE + T.tid);
         }
+    }
+}
+// ... and publish them to the per-point vectors afterwards
+__device__ __forceinline__ void saved_vectors_commit(const TileTC& T, const float (&reg)[13]) {
+    constexpr int vecs[kSavedVecs] = {scr::PV_SDF, scr::PV_COL0, scr::PV_COL1, scr::PV_COL2, scr::PV_GX0, scr::PV_GX1, scr::PV_GX2,
+                                      scr::PV_SIG, scr::PV_CF, scr::PV_UN, scr::PV_NS0, scr::PV_NS1, scr::PV_NS2};
+    if (T.tid < M_TILE) {
+#pragma unroll
+        for (int i = 0; i < kSavedVecs; ++i) T.pv(vecs[i])[T.tid] = reg[i];
     }
 }
 

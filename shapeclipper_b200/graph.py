@@ -88,6 +88,10 @@ class HotPathGraph(nn.Module):
     # ------------------------------------------------------------------------------------------------------
     def compute_loss(self, opt, var, training=False):
         lw, fns = opt.loss_weight, self.loss_fns
+        fused = (var.rgb_recon.is_cuda and fns.mask_mse == 0. and lw.render is not None and lw.mask is not None
+                 and lw.normal is not None and getattr(opt.reg, "fused_losses", True))
+        if fused:
+            return self._compute_loss_fused(opt, var, training)
         L = {}
         if lw.render is not None:
             L["render"] = fns.MSE_loss(var.rgb_recon, var.rgb_input)
@@ -109,5 +113,25 @@ class HotPathGraph(nn.Module):
                 target = inp["normal_input"] @ var["pose_" + tag][..., :3]
                 L["nearest_normal"] = L["nearest_normal"] + fns.normal_loss(var["normal_recon_" + tag], target, valid,
                                                                             tolerance=opt.reg.normal_tol)
+        L["all"] = loss_mod.summarize_loss(opt, L)
+        return L
+
+    def _compute_loss_fused(self, opt, var, training):
+        """Same losses through the fused CUDA kernels (loss.fused_render_losses): two launches + one sort per render."""
+        lw, fns = opt.loss_weight, self.loss_fns
+        eik = var.grad_eikonal if (lw.eikonal is not None and training) else None
+        L = loss_mod.fused_render_losses(fns, var.rgb_recon, var.mask_recon, var.normal_recon, eik, var.rgb_input,
+                                         var.mask_input, var.normal_transformed, opt.reg.normal_tol)
+        if training and lw.nearest_img is not None:
+            L["nearest_img"], L["nearest_mask"], L["nearest_normal"] = 0, 0, 0
+            for v in range(opt.reg.n_views):
+                tag = "NN_%d" % v
+                inp = var["input_" + tag]
+                target = inp["normal_input"] @ var["pose_" + tag][..., :3]
+                N = loss_mod.fused_render_losses(fns, var["rgb_recon_" + tag], var["mask_recon_" + tag], var["normal_recon_" + tag],
+                                                 None, inp["rgb_input"], inp["mask_input"], target, opt.reg.normal_tol)
+                L["nearest_img"] = L["nearest_img"] + N["render"]
+                L["nearest_mask"] = L["nearest_mask"] + N["mask"]
+                L["nearest_normal"] = L["nearest_normal"] + N["normal"]
         L["all"] = loss_mod.summarize_loss(opt, L)
         return L

@@ -81,3 +81,37 @@ def test_graph_replay_matches_eager_step():
     l2 = float(graphed()["all"])
     assert l1 != l2 and l2 == l2
     assert graphed.launches_per_step >= 10
+
+
+def test_fused_render_losses_match_torch_losses():
+    """sc_render_losses_pass1/2 (model/loss.py:19-97 fused) against the torch restatement in loss.py (itself pinned to the
+    reference by tests/golden/losses.pt): the four loss values and every input gradient."""
+    from shapeclipper_b200 import loss as loss_mod, options
+    opt = options.default_options()
+    fns = loss_mod.Loss(opt)
+    torch.manual_seed(3)
+    B, R = 3, 700
+    dev = "cuda"
+    base = dict(rgb=torch.rand(B, R, 3), mask=torch.rand(B, R, 1), normal=torch.nn.functional.normalize(torch.randn(B, R, 3), dim=-1),
+                eik=1 + 0.1 * torch.randn(B * 2 * R), normal_t=torch.nn.functional.normalize(torch.randn(B, R, 3), dim=-1))
+    rgb_t, mask_t = torch.rand(B, R, 3, device=dev), (torch.rand(B, R, 1, device=dev) > 0.4).float()
+    w = torch.tensor([1.0, 0.5, 0.01, 0.03], device=dev)
+    res = []
+    for fused in (True, False):
+        x = {k: v.clone().to(dev).requires_grad_(True) for k, v in base.items()}
+        if fused:
+            L = loss_mod.fused_render_losses(fns, x["rgb"], x["mask"], x["normal"], x["eik"], rgb_t, mask_t, x["normal_t"], opt.reg.normal_tol)
+        else:
+            valid = (mask_t > 0.5) & (x["mask"] > 0.5)
+            L = dict(render=fns.MSE_loss(x["rgb"], rgb_t), mask=fns.mask_loss(x["mask"], mask_t),
+                     normal=fns.normal_loss(x["normal"], x["normal_t"], valid, tolerance=opt.reg.normal_tol),
+                     eikonal=fns.MSE_loss(x["eik"].view(B, -1), 1))
+        tot = w[0] * L["render"] + w[1] * L["mask"] + w[2] * L["normal"] + w[3] * L["eikonal"]
+        tot.backward()
+        res.append(({k: float(v) for k, v in L.items()}, {k: v.grad.clone() for k, v in x.items()}))
+    for k in ("render", "mask", "normal", "eikonal"):
+        a, b = res[0][0][k], res[1][0][k]
+        assert abs(a - b) <= 2e-6 * max(1.0, abs(b)), (k, a, b)
+    for k in base:
+        ga, gb = res[0][1][k], res[1][1][k]
+        assert float((ga - gb).abs().max()) <= 1e-6 * max(float(gb.abs().max()), 1e-6) + 1e-9, k
