@@ -175,19 +175,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
             float* cbb = a.cb_bar + (size_t)T.b * kCbRows * 64;
             __syncthreads();
             T.mark();                                                            // [trace] tile start
-            float pvreg[13], ubreg[8];
-            if (use_saved) {     // every global load of the tile prologue is issued before the set-up arithmetic: one HBM latency, overlapped
-                st = reinterpret_cast<float*>(a.saved) + (size_t)tile * TS_SAVED_PLANES * kStashPlane;
-                saved_vectors_prefetch(T, st + TS_SAVED_PV * kStashPlane, pvreg);
-                if (MODE == 0) {
-                    if (tid < T.rays_per_tile) load_upstream(a, T.b, T.first + tid, ubreg);
-                    st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);             // r2, consumed after the ray phase
-                }
-            }
             tc_tile_setup<MODE>(T, a);
             T.mark();                                                            // [trace] setup done
             if (use_saved) {
-                saved_vectors_commit(T, pvreg);
+                st = reinterpret_cast<float*>(a.saved) + (size_t)tile * TS_SAVED_PLANES * kStashPlane;
+                if (MODE == 0) st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);      // r2, consumed after the ray phase: HBM latency hidden
+                saved_vectors<false>(T, st + TS_SAVED_PV * kStashPlane);
                 __syncthreads();
                 T.mark();                                                        // [trace] saved vectors loaded
             } else {
@@ -207,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 }
                 __syncthreads();
             } else {
-                ray_phase_backward(T, a, vacc + VA_BETA, kThreads, use_saved ? ubreg : nullptr);
+                ray_phase_backward(T, a, vacc + VA_BETA, kThreads);
                 T.mark();                                                        // [trace] ray phase done
 
                 // ============================================================================ RGB backward
