@@ -87,59 +87,73 @@ __global__ void layernorm_kernel(const float* __restrict__ x, size_t row_stride,
     }
 }
 
-// softmax(q k^T / sqrt(64)) v per (image, head); qkv fp32 [B*T, 3W] (q | k | v), head h = columns h*64..h*64+63
+// softmax(q k^T / sqrt(64)) v per (image, head); qkv fp32 [B*T, 3W] (q | k | v), head h = columns h*64..h*64+63.
+// K and V of the head sit in shared memory with 16-byte-aligned rows (stride 68 floats: conflict-free LDS.128 for 8 lanes on
+// consecutive keys); a warp takes TWO query rows per pass so that every K / V vector load feeds two accumulators.
+constexpr int kAttLd = 68;
 __global__ void attention_kernel(const float* __restrict__ qkv, int T, int W, bf16* __restrict__ hi, bf16* __restrict__ lo)
 {
-    extern __shared__ float sm[];
-    float* Ks = sm;                 // [T][65]
-    float* Vs = sm + (size_t)T * 65;
-    float* Ps = Vs + (size_t)T * 65;   // [warps][T + 64]
+    extern __shared__ __align__(16) float sm[];
+    float* Ks = sm;                          // [T][68]
+    float* Vs = sm + (size_t)T * kAttLd;
+    float* Ps = Vs + (size_t)T * kAttLd;     // per warp: P0[Tp] P1[Tp] Q0[64] Q1[64]
+    const int Tp = (T + 3) & ~3;
     const int b = blockIdx.x, h = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const float* base = qkv + (size_t)b * T * 3 * W + h * 64;
-    for (int i = threadIdx.x; i < T * 64; i += blockDim.x) {
-        const int t = i >> 6, d = i & 63;
-        Ks[t * 65 + d] = base[(size_t)t * 3 * W + W + d];
-        Vs[t * 65 + d] = base[(size_t)t * 3 * W + 2 * W + d];
+    for (int i = threadIdx.x; i < T * 16; i += blockDim.x) {                 // float4 granularity: 16 per row
+        const int t = i >> 4, d4 = (i & 15) << 2;
+        *reinterpret_cast<float4*>(Ks + t * kAttLd + d4) = *reinterpret_cast<const float4*>(base + (size_t)t * 3 * W + W + d4);
+        *reinterpret_cast<float4*>(Vs + t * kAttLd + d4) = *reinterpret_cast<const float4*>(base + (size_t)t * 3 * W + 2 * W + d4);
     }
     __syncthreads();
-    float* P = Ps + (size_t)warp * (T + 64);
-    float* Qw = P + T;                 // this warp's query row, pre-scaled by 1/sqrt(64)
-    for (int tq = warp; tq < T; tq += nw) {
-        Qw[lane] = base[(size_t)tq * 3 * W + lane] * 0.125f;
-        Qw[32 + lane] = base[(size_t)tq * 3 * W + 32 + lane] * 0.125f;
+    float* P0 = Ps + (size_t)warp * (2 * Tp + 128);
+    float* P1 = P0 + Tp;
+    float* Q0 = P1 + Tp;
+    float* Q1 = Q0 + 64;
+    for (int tq = 2 * warp; tq < T; tq += 2 * nw) {
+        const bool two = tq + 1 < T;
+        const float* q0 = base + (size_t)tq * 3 * W;
+        const float* q1 = base + (size_t)(two ? tq + 1 : tq) * 3 * W;
+        Q0[lane] = q0[lane] * 0.125f; Q0[32 + lane] = q0[32 + lane] * 0.125f;          // pre-scaled by 1/sqrt(64)
+        Q1[lane] = q1[lane] * 0.125f; Q1[32 + lane] = q1[32 + lane] * 0.125f;
         __syncwarp();
-        float mx = -INFINITY;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
         for (int tk = lane; tk < T; tk += 32) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;                 // four independent chains: the dot is latency-bound
-            const float* kr = Ks + tk * 65;
+            const float4* kr = reinterpret_cast<const float4*>(Ks + tk * kAttLd);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
 #pragma unroll
-            for (int d = 0; d < 64; d += 4) {
-                s0 = fmaf(Qw[d], kr[d], s0); s1 = fmaf(Qw[d + 1], kr[d + 1], s1);
-                s2 = fmaf(Qw[d + 2], kr[d + 2], s2); s3 = fmaf(Qw[d + 3], kr[d + 3], s3);
+            for (int d = 0; d < 16; ++d) {
+                const float4 k = kr[d];
+                const float4 x = reinterpret_cast<const float4*>(Q0)[d];
+                const float4 y = reinterpret_cast<const float4*>(Q1)[d];
+                a0 = fmaf(x.x, k.x, a0); a1 = fmaf(x.y, k.y, a1); a2 = fmaf(x.z, k.z, a2); a3 = fmaf(x.w, k.w, a3);
+                c0 = fmaf(y.x, k.x, c0); c1 = fmaf(y.y, k.y, c1); c2 = fmaf(y.z, k.z, c2); c3 = fmaf(y.w, k.w, c3);
             }
-            const float s = (s0 + s1) + (s2 + s3);
-            P[tk] = s; mx = fmaxf(mx, s);
+            const float s0 = (a0 + a1) + (a2 + a3), s1 = (c0 + c1) + (c2 + c3);
+            P0[tk] = s0; P1[tk] = s1;
+            mx0 = fmaxf(mx0, s0); mx1 = fmaxf(mx1, s1);
         }
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int tk = lane; tk < T; tk += 32) { const float e = __expf(P[tk] - mx); P[tk] = e; sum += e; }
-        sum = warp_sum(sum);
+        mx0 = warp_max(mx0); mx1 = warp_max(mx1);
+        float sum0 = 0.f, sum1 = 0.f;
+        for (int tk = lane; tk < T; tk += 32) {
+            const float e0 = __expf(P0[tk] - mx0), e1 = __expf(P1[tk] - mx1);
+            P0[tk] = e0; P1[tk] = e1; sum0 += e0; sum1 += e1;
+        }
+        sum0 = warp_sum(sum0); sum1 = warp_sum(sum1);
         __syncwarp();
-        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-        int tk = 0;
-        for (; tk + 1 < T; tk += 2) {
-            const float p = P[tk], q = P[tk + 1];
-            o0 = fmaf(p, Vs[tk * 65 + lane], o0);
-            o1 = fmaf(p, Vs[tk * 65 + 32 + lane], o1);
-            o2 = fmaf(q, Vs[(tk + 1) * 65 + lane], o2);
-            o3 = fmaf(q, Vs[(tk + 1) * 65 + 32 + lane], o3);
+        // out[d] for d = 2 lane, 2 lane + 1 (one 8-byte V load per key feeds both queries)
+        float o00 = 0.f, o01 = 0.f, o10 = 0.f, o11 = 0.f;
+#pragma unroll 4
+        for (int tk = 0; tk < T; ++tk) {
+            const float2 v = *reinterpret_cast<const float2*>(Vs + tk * kAttLd + 2 * lane);
+            const float p0 = P0[tk], p1 = P1[tk];
+            o00 = fmaf(p0, v.x, o00); o01 = fmaf(p0, v.y, o01);
+            o10 = fmaf(p1, v.x, o10); o11 = fmaf(p1, v.y, o11);
         }
-        if (tk < T) { const float p = P[tk]; o0 = fmaf(p, Vs[tk * 65 + lane], o0); o1 = fmaf(p, Vs[tk * 65 + 32 + lane], o1); }
-        o0 += o2; o1 += o3;
-        const float inv = 1.f / sum;
-        const size_t o = ((size_t)b * T + tq) * W + h * 64;
-        split_store(hi, lo, o + lane, o0 * inv);
-        split_store(hi, lo, o + 32 + lane, o1 * inv);
+        const float i0 = 1.f / sum0, i1 = 1.f / sum1;
+        const size_t o = ((size_t)b * T + tq) * W + h * 64 + 2 * lane;
+        split_store(hi, lo, o, o00 * i0); split_store(hi, lo, o + 1, o01 * i0);
+        if (two) { split_store(hi, lo, o + W, o10 * i1); split_store(hi, lo, o + W + 1, o11 * i1); }
         __syncwarp();
     }
 }
@@ -254,7 +268,7 @@ extern "C" int sc_clip_encode(const ScClipConfig* cfg, const ScClipWeights* wts,
         SC_TRY(sc_gemm_bf16_tc(w.ln_hi, lo(w.ln_lo), L.qkv_w_hi, wlo(L.qkv_w_lo), M, 3 * W, W, L.qkv_b, nullptr, 0, 1.f,
                                w.qkv, nullptr, nullptr, stream));
         const int att_threads = 512;      // 16 warps share one (image, head)'s K/V tile: ~3 query rows per warp at T = 50
-        const size_t att_smem = ((size_t)2 * T * 65 + (size_t)(att_threads / 32) * (T + 64)) * sizeof(float);
+        const size_t att_smem = ((size_t)2 * T * scclip::kAttLd + (size_t)(att_threads / 32) * (2 * ((T + 3) & ~3) + 128)) * sizeof(float);
         if (att_smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)att_smem);
             if (e != cudaSuccess) return (int)e;
