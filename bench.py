@@ -159,8 +159,8 @@ def workload_config(a, opt, clip):
     return dict(workload="configs[1]: batch=%d/GPU Pix3D-shaped synthetic, %d rays x %d samples, k_nearest=%d, n_views=%d, "
                          "render+losses+backward+Adam%s" % (a.batch, int(opt.render.rand_sample), opt.render.n_samples_uniform,
                                                             opt.data.k_nearest, opt.reg.n_views, "+CLIP ViT-B/32" if clip else ""),
-                per_gpu_batch=a.batch, image_size=[opt.H, opt.W], l2="inputs cycle through 4 distinct batches; the kernels' "
-                "working set (per-CTA scratch, 128 MB) exceeds L2", parallelism="dp%d" % a.gpus, clip=clip)
+                per_gpu_batch=a.batch, image_size=[opt.H, opt.W], l2="inputs cycle through 4 distinct batches; the render kernels' "
+                "working set per step (2 x 1.97 GB of saved activations + 97 MB of per-CTA scratch) exceeds the 126 MB L2", parallelism="dp%d" % a.gpus, clip=clip)
 
 
 # --------------------------------------------------------------------------------------------------- our arm

@@ -81,7 +81,7 @@ class HotPathGraph(nn.Module):
             var["pose_" + tag], var["intr_" + tag], var["scale_dist_" + tag] = pose, intr, scale_dist
             # the QUERY's shape code, the neighbour's appearance code and viewpoint (model/graph.py:207-209)
             rgb, mask, _, depth, normal, _ = self.renderer(opt, pose, intr, scale_dist, var.proj_latent_sdf, z_rgb,
-                                                           ray_idx=ray_idx, training=training)
+                                                           ray_idx=ray_idx, training=training, eikonal=False)
             var["rgb_recon_" + tag], var["mask_recon_" + tag] = rgb, mask
             var["depth_recon_" + tag], var["normal_recon_" + tag] = depth, normal
 

@@ -67,7 +67,10 @@ class Renderer(nn.Module):
         return self._t_cache["t"]
 
     def forward(self, opt, pose, intr, scale_dist, proj_latent_sdf, proj_latent_rgb, ray_idx=None, training=True,
-                visualize=False):
+                visualize=False, eikonal=True):
+        """The reference's signature plus `eikonal` (default True = reference behaviour): a caller that discards
+        grad_eikonal — the reference's neighbour-view render, model/graph.py:207 — can pass False to skip the eikonal point
+        queries; the generator draws still happen, so the random stream stays in step with the reference."""
         if opt.camera.model != "perspective":
             raise NotImplementedError("only the perspective camera of the reference config is implemented")
         dev = pose.device
@@ -92,6 +95,7 @@ class Renderer(nn.Module):
         grad_eikonal = None
         if training:
             uni = torch.empty(B * R, 3, device=rng_dev).uniform_(self.eik_range[0], self.eik_range[1]).to(dev).reshape(B, R, 3)
+        if training and eikonal:
             sd_ray = scale_dist.unsqueeze(-1).expand(B, R).reshape(-1)
             u_at = u.gather(1, eik_idx.unsqueeze(-1)).squeeze(-1)
             z_eik = UniformSampler.depth_at(opt, sd_ray, t_vals, eik_idx, u_at).reshape(B, R, 1)
