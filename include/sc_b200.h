@@ -56,6 +56,16 @@ int sc_pixel_rays_backward(const float* pose, const float* intr, const int64_t* 
                            int width, const float* cam_loc_bar, const float* ray_dirs_bar, const float* depth_fac_bar,
                            float* workspace, float* pose_bar, float* intr_bar, cudaStream_t stream);
 
+/* Eikonal sample points (model/renderer.py:154-170): points [B,2R,3] = cat(uniform_pts [B,R,3], cam_loc + z_eik * ray_dirs),
+ * z_eik [B,R] = depth of sample eik_idx [B*R] (int64) of each ray, stratified with jitter [B*R,S] when jitter != NULL
+ * (model/renderer.py:13-37). backward: points_bar -> ray_dirs_bar [B,R,3] and acc [B][4] = (cam_loc_bar xyz, scale_dist_bar). */
+int sc_eikonal_points_forward(const float* cam_loc, const float* ray_dirs, const float* scale_dist, const float* t_vals,
+                              const float* jitter, const int64_t* eik_idx, const float* uniform_pts, int batch, int n_rays,
+                              int n_samples, float cam_dist, float half_range, float* points, float* z_eik,
+                              cudaStream_t stream);
+int sc_eikonal_points_backward(const float* ray_dirs, const float* z_eik, const float* points_bar, int batch, int n_rays,
+                               float cam_dist, float* ray_dirs_bar, float* acc, cudaStream_t stream);
+
 /* ---- render-consuming losses of one render: values and unit gradients -------------
  * Replaces model/loss.py:19-97 as combined in model/graph.py:220-265: MSE(rgb), soft-IoU mask loss, trimmed normal loss,
  * eikonal MSE. pass1 -> (caller: order = stable argsort(key)) -> pass2. rgb / normal [B,R,3], mask [B,R], eik [n_eik]

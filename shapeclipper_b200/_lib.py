@@ -49,6 +49,10 @@ def _declare(L):
     L.sc_pixel_rays_backward.argtypes = [vp, vp, vp, i, i, i, vp, vp, vp, vp, vp, vp, vp]
     L.sc_pixel_rays_backward.restype = i
     f, d = ctypes.c_float, ctypes.c_double
+    L.sc_eikonal_points_forward.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, f, f, vp, vp, vp]
+    L.sc_eikonal_points_forward.restype = i
+    L.sc_eikonal_points_backward.argtypes = [vp, vp, vp, i, i, f, vp, vp, vp]
+    L.sc_eikonal_points_backward.restype = i
     L.sc_render_losses_workspace_floats.argtypes = [i]
     L.sc_render_losses_workspace_floats.restype = sz
     L.sc_render_losses_pass1.argtypes = [vp, vp, vp, vp, vp, vp, vp, i, i, i, f, vp, vp, vp, vp, vp, vp, vp, vp]

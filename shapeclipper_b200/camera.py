@@ -69,6 +69,51 @@ class _PixelRays(torch.autograd.Function):
         return pose_bar, intr_bar, None, None, None
 
 
+class _EikonalPoints(torch.autograd.Function):
+    """cat(uniform points, cam_loc + z_eik * ray_dirs) [B*2R,3] (model/renderer.py:154-170), one launch each way."""
+
+    @staticmethod
+    def forward(ctx, cam_loc, ray_dirs, scale_dist, t_vals, jitter, eik_idx, uniform_pts, cam_dist, half_range):
+        from . import _lib, _render_native as rn
+        L = _lib.lib()
+        _lib.require_cuda(cam_loc, ray_dirs, scale_dist, t_vals, jitter, eik_idx, uniform_pts)
+        B, R = ray_dirs.shape[0], ray_dirs.shape[1]
+        S = t_vals.shape[0]
+        dev = ray_dirs.device
+        c = lambda t: rn._f32c(t.detach()) if t is not None else None
+        loc, dirs, sd, tv, jit, uni = c(cam_loc), c(ray_dirs), c(scale_dist), c(t_vals), c(jitter), c(uniform_pts)
+        idx = eik_idx.contiguous()
+        pts = torch.empty(B, 2 * R, 3, device=dev); z = torch.empty(B, R, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.sc_eikonal_points_forward(_lib.ptr(loc), _lib.ptr(dirs), _lib.ptr(sd), _lib.ptr(tv), _lib.ptr(jit), _lib.ptr(idx),
+                                                   _lib.ptr(uni), B, R, S, float(cam_dist), float(half_range), _lib.ptr(pts), _lib.ptr(z),
+                                                   _lib.stream_of(dirs)), "sc_eikonal_points_forward")
+        rn.TIMERS.count()
+        ctx.save_for_backward(dirs, z)
+        ctx.cam_dist = float(cam_dist)
+        return pts.reshape(-1, 3)
+
+    @staticmethod
+    def backward(ctx, g_pts):
+        from . import _lib, _render_native as rn
+        L = _lib.lib()
+        dirs, z = ctx.saved_tensors
+        B, R = dirs.shape[0], dirs.shape[1]
+        dev = dirs.device
+        g = rn._f32c(g_pts)
+        dirs_bar = torch.empty(B, R, 3, device=dev); acc = torch.empty(B, 4, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.sc_eikonal_points_backward(_lib.ptr(dirs), _lib.ptr(z), _lib.ptr(g), B, R, ctx.cam_dist, _lib.ptr(dirs_bar),
+                                                    _lib.ptr(acc), _lib.stream_of(dirs)), "sc_eikonal_points_backward")
+        rn.TIMERS.count()
+        return acc[:, :3], dirs_bar, acc[:, 3], None, None, None, None, None, None
+
+
+def eikonal_points(cam_loc, ray_dirs, scale_dist, t_vals, jitter, eik_idx, uniform_pts, cam_dist, half_range=0.7):
+    """[B*2R,3] eikonal sample points of one render (fused CUDA path)."""
+    return _EikonalPoints.apply(cam_loc, ray_dirs, scale_dist, t_vals, jitter, eik_idx, uniform_pts, cam_dist, half_range)
+
+
 def pixel_rays_torch(pose, intr, H, W, ray_idx=None):
     """pose [B,3,4] world->camera, intr [B,3,3]; ray_idx [B,R] int64 flat pixel ids (row-major) or None = all.
     -> cam_loc [B,3], unit ray_dirs [B,R,3], depth_fac [B,R] (ray length -> depth factor)."""

@@ -168,3 +168,102 @@ extern "C" int sc_pixel_rays_backward(const float* pose, const float* intr, cons
     scrays::rays_bwd_finish_kernel<<<(batch + 63) / 64, 64, 0, stream>>>(pose, intr, workspace, cam_loc_bar, batch, pose_bar, intr_bar);
     return (int)cudaGetLastError();
 }
+
+// ---- eikonal sample points (model/renderer.py:154-170 + UniformSampler.get_z_vals's z_eik, model/renderer.py:13-37) --------
+// pts [B, 2R, 3] = cat( uniform points uni [B,R,3],  cam_loc + z_eik * ray_dirs )  with z_eik = the depth of the randomly picked
+// sample eik_idx of each ray (stratified with jitter u when u != NULL). In torch this is ~45 launches forward and ~40 backward.
+namespace scrays {
+
+__device__ __forceinline__ float eik_depth(float sd, float cam_dist, float half_range, const float* __restrict__ t_vals, int S,
+                                           int idx, const float* __restrict__ u_row)
+{
+    // the same un-contracted fp32 operations as the render kernel's depth set-up (and torch's elementwise ops)
+    const float c = __fmul_rn(cam_dist, sd), nr = __fsub_rn(c, half_range), fr = __fadd_rn(c, half_range);
+    auto zb = [&](int i) {
+        const float t = t_vals[min(max(i, 0), S - 1)];
+        return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.f, t)), __fmul_rn(fr, t));
+    };
+    const float z = zb(idx);
+    if (u_row == nullptr) return z;
+    const float up = (idx < S - 1) ? __fmul_rn(0.5f, __fadd_rn(zb(idx + 1), z)) : z;
+    const float lo = (idx > 0) ? __fmul_rn(0.5f, __fadd_rn(z, zb(idx - 1))) : z;
+    return __fadd_rn(lo, __fmul_rn(__fsub_rn(up, lo), u_row[idx]));
+}
+
+__global__ void eik_points_fwd_kernel(const float* __restrict__ cam_loc, const float* __restrict__ dirs, const float* __restrict__ sd,
+                                      const float* __restrict__ t_vals, const float* __restrict__ u, const int64_t* __restrict__ eik_idx,
+                                      const float* __restrict__ uni, int R, int S, float cam_dist, float half_range,
+                                      float* __restrict__ pts, float* __restrict__ z_out)
+{
+    const int b = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const size_t g = (size_t)b * R + r;
+    const int idx = (int)eik_idx[g];
+    const float z = eik_depth(sd[b], cam_dist, half_range, t_vals, S, idx, u ? u + g * S : nullptr);
+    z_out[g] = z;
+    float* pu = pts + ((size_t)b * 2 * R + r) * 3;
+    float* pn = pts + ((size_t)b * 2 * R + R + r) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { pu[c] = uni[g * 3 + c]; pn[c] = __fadd_rn(cam_loc[b * 3 + c], __fmul_rn(z, dirs[g * 3 + c])); }
+}
+
+// pts_bar [B,2R,3] -> dirs_bar [B,R,3] (written), cam_loc_bar [B,3], sd_bar [B] (atomics; zeroed by the launcher)
+__global__ void eik_points_bwd_kernel(const float* __restrict__ dirs, const float* __restrict__ z_eik, const float* __restrict__ pts_bar,
+                                      int R, float cam_dist, float* __restrict__ dirs_bar, float* __restrict__ acc /*[B][4]*/)
+{
+    const int b = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < R) {
+        const size_t g = (size_t)b * R + r;
+        const float* pb = pts_bar + ((size_t)b * 2 * R + R + r) * 3;
+        const float z = z_eik[g];
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { v[c] = pb[c]; dirs_bar[g * 3 + c] = z * pb[c]; dot += dirs[g * 3 + c] * pb[c]; }
+        v[3] = cam_dist * dot;                       // d z_eik / d scale_dist = cam_dist for every sample (convex combination of bin edges)
+    }
+    __shared__ float red[8][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float s = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) red[warp][i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float s = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+        atomicAdd(acc + b * 4 + threadIdx.x, s);
+    }
+}
+
+}  // namespace scrays
+
+extern "C" int sc_eikonal_points_forward(const float* cam_loc, const float* ray_dirs, const float* scale_dist, const float* t_vals,
+                                         const float* jitter, const int64_t* eik_idx, const float* uniform_pts, int batch, int n_rays,
+                                         int n_samples, float cam_dist, float half_range, float* points, float* z_eik,
+                                         cudaStream_t stream)
+{
+    if (batch <= 0 || n_rays <= 0) return 0;
+    if (!cam_loc || !ray_dirs || !scale_dist || !t_vals || !eik_idx || !uniform_pts || !points || !z_eik || n_samples <= 0)
+        return (int)cudaErrorInvalidValue;
+    dim3 grid((n_rays + 255) / 256, batch);
+    scrays::eik_points_fwd_kernel<<<grid, 256, 0, stream>>>(cam_loc, ray_dirs, scale_dist, t_vals, jitter, eik_idx, uniform_pts, n_rays,
+                                                            n_samples, cam_dist, half_range, points, z_eik);
+    return (int)cudaGetLastError();
+}
+
+// acc: batch * 4 floats (cam_loc_bar xyz, scale_dist_bar), zeroed here
+extern "C" int sc_eikonal_points_backward(const float* ray_dirs, const float* z_eik, const float* points_bar, int batch, int n_rays,
+                                          float cam_dist, float* ray_dirs_bar, float* acc, cudaStream_t stream)
+{
+    if (batch <= 0 || n_rays <= 0) return 0;
+    if (!ray_dirs || !z_eik || !points_bar || !ray_dirs_bar || !acc) return (int)cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)batch * 4 * sizeof(float), stream);
+    if (e != cudaSuccess) return (int)e;
+    dim3 grid((n_rays + 255) / 256, batch);
+    scrays::eik_points_bwd_kernel<<<grid, 256, 0, stream>>>(ray_dirs, z_eik, points_bar, n_rays, cam_dist, ray_dirs_bar, acc);
+    return (int)cudaGetLastError();
+}

@@ -96,11 +96,7 @@ class Renderer(nn.Module):
         if training:
             uni = torch.empty(B * R, 3, device=rng_dev).uniform_(self.eik_range[0], self.eik_range[1]).to(dev).reshape(B, R, 3)
         if training and eikonal:
-            sd_ray = scale_dist.unsqueeze(-1).expand(B, R).reshape(-1)
-            u_at = u.gather(1, eik_idx.unsqueeze(-1)).squeeze(-1)
-            z_eik = UniformSampler.depth_at(opt, sd_ray, t_vals, eik_idx, u_at).reshape(B, R, 1)
-            near_pts = cam_loc.unsqueeze(1) + z_eik * ray_dirs
-            eik_pts = torch.cat([uni, near_pts], dim=1).reshape(-1, 3)
+            eik_pts = camera.eikonal_points(cam_loc, ray_dirs, scale_dist, t_vals, u, eik_idx, uni, opt.camera.dist)
             _, _, g = self.sdf_network.get_conditional_output(opt, B, eik_pts, proj_latent_sdf, compute_grad=True)
             grad_eikonal = g.norm(2, dim=1)
         if visualize:

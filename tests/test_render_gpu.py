@@ -293,3 +293,35 @@ def test_fused_pixel_rays_match_torch_restatement(use_idx):
         outs.append((c, d, f, p.grad, k.grad))
     for name, a, w in zip(("center", "dirs", "depth_fac", "pose.grad", "intr.grad"), outs[0], outs[1]):
         _close(a, w, name, 2e-5)
+
+
+def test_fused_eikonal_points_match_torch_restatement():
+    """sc_eikonal_points_forward / _backward (model/renderer.py:13-37,154-170) against the torch ops they replace."""
+    from shapeclipper_b200 import camera, options
+    from shapeclipper_b200.renderer import UniformSampler
+    opt = options.default_options()
+    torch.manual_seed(8)
+    B, Rn, S = 3, 200, 64
+    dev = "cuda"
+    t_vals = torch.linspace(0., 1., S, device=dev)
+    u = torch.rand(B * Rn, S, device=dev)
+    idx = torch.randint(S, (B * Rn,), device=dev)
+    idx[:4] = torch.tensor([0, S - 1, 0, S - 1], device=dev)                  # both ends of the stratification
+    uni = torch.rand(B, Rn, 3, device=dev) * 2 - 1
+    res = []
+    for fused in (True, False):
+        loc = torch.randn(B, 3, device=dev, generator=None).mul_(0).add_(torch.tensor([[0.1, -4.9, 0.3]], device=dev)).requires_grad_(True)
+        dirs = torch.nn.functional.normalize(torch.randn(B, Rn, 3, generator=torch.Generator().manual_seed(1)), dim=-1).to(dev).requires_grad_(True)
+        sd = (1 + 0.1 * torch.rand(B, generator=torch.Generator().manual_seed(2))).to(dev).requires_grad_(True)
+        if fused:
+            pts = camera.eikonal_points(loc, dirs, sd, t_vals, u, idx, uni, opt.camera.dist)
+        else:
+            sd_ray = sd.unsqueeze(-1).expand(B, Rn).reshape(-1)
+            u_at = u.gather(1, idx.unsqueeze(-1)).squeeze(-1)
+            z = UniformSampler.depth_at(opt, sd_ray, t_vals, idx, u_at).reshape(B, Rn, 1)
+            pts = torch.cat([uni, loc.unsqueeze(1) + z * dirs], dim=1).reshape(-1, 3)
+        w = torch.randn(pts.shape, generator=torch.Generator().manual_seed(3)).to(dev)
+        (pts * w).sum().backward()
+        res.append((pts.detach(), loc.grad, dirs.grad, sd.grad))
+    for name, a, b in zip(("points", "cam_loc.grad", "ray_dirs.grad", "scale_dist.grad"), res[0], res[1]):
+        _close(a, b, name, 2e-6)
