@@ -174,17 +174,22 @@ __global__ void l2norm_kernel(const float* __restrict__ x, int rows, int D, floa
     }
 }
 
-// top-k (largest, k <= 16) of each row of sim [Q, N]; ties -> lowest index. One warp per row.
+// top-k (largest, k <= 16) of each row of sim [Q, N]; ties -> lowest index. One 256-thread CTA per row: k rounds of a
+// block-wide argmax over the entries strictly after the previous winner in (value desc, index asc) order.
 __global__ void topk_kernel(const float* __restrict__ sim, int Q, int ld, int N, int k, float* __restrict__ val,
                             int32_t* __restrict__ idx)
 {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     if (row >= Q) return;
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    __shared__ float wv;
+    __shared__ int wi;
     const float* s = sim + (size_t)row * ld;
     float prev_v = INFINITY; int prev_i = -1;
     for (int j = 0; j < k; ++j) {
         float bv = -INFINITY; int bi = 0x7fffffff;
-        for (int c = lane; c < N; c += 32) {
+        for (int c = threadIdx.x; c < N; c += blockDim.x) {
             const float v = s[c];
             const bool after_prev = (v < prev_v) || (v == prev_v && c > prev_i);     // strictly after the previous winner
             if (after_prev && (v > bv || (v == bv && c < bi))) { bv = v; bi = c; }
@@ -195,8 +200,16 @@ __global__ void topk_kernel(const float* __restrict__ sim, int Q, int ld, int N,
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
-        if (lane == 0) { val[(size_t)row * k + j] = bv; idx[(size_t)row * k + j] = bi; }
-        prev_v = bv; prev_i = bi;
+        if (lane == 0) { sv[warp] = bv; si[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float fv = sv[0]; int fi = si[0];
+            for (int w = 1; w < nw; ++w) if (sv[w] > fv || (sv[w] == fv && si[w] < fi)) { fv = sv[w]; fi = si[w]; }
+            wv = fv; wi = fi;
+            val[(size_t)row * k + j] = fv; idx[(size_t)row * k + j] = fi;
+        }
+        __syncthreads();
+        prev_v = wv; prev_i = wi;
     }
 }
 
@@ -302,6 +315,6 @@ extern "C" int sc_cosine_topk(const void* q_hi, const void* q_lo, const void* ba
     if (k <= 0 || n_bank_valid > n_bank || k > n_bank_valid || sim_workspace == nullptr) return (int)cudaErrorInvalidValue;
     SC_TRY(sc_gemm_bf16_tc(q_hi, q_lo, bank_hi, bank_lo, n_query, n_bank, dim, nullptr, nullptr, 0, 1.f, sim_workspace, nullptr,
                            nullptr, stream));
-    topk_kernel<<<(n_query + 7) / 8, 256, 0, stream>>>(sim_workspace, n_query, n_bank, n_bank_valid, k, values, indices);
+    topk_kernel<<<n_query, 256, 0, stream>>>(sim_workspace, n_query, n_bank, n_bank_valid, k, values, indices);
     return (int)cudaGetLastError();
 }
