@@ -24,13 +24,16 @@ GRAD_LEAVES = ("pose", "intr", "scale_dist", "proj_latent_sdf", "proj_latent_rgb
 
 class TrainStep:
     def __init__(self, opt, graph, optim, flat_grads, example_batch, device, side_work=None, use_cuda_graph=True,
-                 warmup=3):
+                 warmup=3, side_stream=True):
         """graph: HotPathGraph; flat_grads: dist.FlatGradients over the optimiser's parameters; example_batch: a host
         batch (synthetic.make_batch layout) fixing every shape; side_work: optional callable run at the start of each
         step on the same stream (bench.py: the CLIP encode + k-NN leg)."""
         self.opt, self.graph, self.optim, self.flat = opt, graph, optim, flat_grads
         self.device = torch.device(device)
         self.side_work = side_work
+        # side_work (independent of the render path) runs on its own low-priority stream, forked at the start of the step and
+        # joined after the backward: its kernels fill the SMs the small glue kernels between the render launches leave idle
+        self._side = torch.cuda.Stream(self.device) if (side_work is not None and side_stream) else None
         self.var = Options()
         for k, t in example_batch.items():
             d = t.to(self.device)
@@ -60,8 +63,14 @@ class TrainStep:
         for k in GRAD_LEAVES:
             if k in self.var:
                 self.var[k].grad = None
+        main = torch.cuda.current_stream(self.device)
         if self.side_work is not None:
-            self.side_work()
+            if self._side is not None:
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    self.side_work()
+            else:
+                self.side_work()
         # parameter gradients go straight into the flat buffer's views (render_fn.FUSED_GRAD_ACCUMULATION)
         old, render_fn.FUSED_GRAD_ACCUMULATION = render_fn.FUSED_GRAD_ACCUMULATION, True
         try:
@@ -69,6 +78,8 @@ class TrainStep:
             loss["all"].backward()
         finally:
             render_fn.FUSED_GRAD_ACCUMULATION = old
+        if self.side_work is not None and self._side is not None:
+            main.wait_stream(self._side)
         return loss
 
     def _capture(self, warmup):
