@@ -85,6 +85,7 @@ __device__ __forceinline__ void ray_phase_backward(TT& T, const ScRenderArgs& a,
                     for (int c = 0; c < 8; ++c) ub[c] = u8[c];
                 }
                 __syncthreads();
+                T.mark();
                 float delta = 0.f, E = 0.f, Tr = 0.f, ea = 0.f, w = 0.f, wp = 0.f, z = 0.f, fac = 0.f;
                 int rl = 0;
                 if (tid < M_TILE) {
@@ -103,6 +104,7 @@ __device__ __forceinline__ void ray_phase_backward(TT& T, const ScRenderArgs& a,
                     }
                 }
                 __syncthreads();
+                T.mark();
                 if (tid < T.rays_per_tile) {
                     const int r = T.first + tid;
                     const float* ac = T.ray + RAYX_ACC + tid * 8;
@@ -121,6 +123,7 @@ __device__ __forceinline__ void ray_phase_backward(TT& T, const ScRenderArgs& a,
                     if (r < a.n_per_image) a.depth_fac_bar[(size_t)T.b * a.n_per_image + r] = ub[4] * ac[0];
                 }
                 __syncthreads();
+                T.mark();
                 if (tid < M_TILE) {
                     const int p = tid, S = T.S, s = p % S;
                     const float* ub = T.ray + RAYX_BAR + rl * 8;
@@ -171,6 +174,7 @@ __device__ __forceinline__ void ray_phase_backward(TT& T, const ScRenderArgs& a,
                     if (lane == 0) atomicAdd(part_beta, bb);
                 }
                 __syncthreads();
+                T.mark();
 }
 
 }  // namespace scr

@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                     }
                 }
                 __syncthreads();
+                T.mark();                                                        // [trace] o3_bar done
                 // o2_bar = (V3^T o3_bar) * [r2 > 0] -> Y ; dV3 += o3_bar (x) r2
                 if (!use_saved) st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);
                 {
@@ -401,6 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
             T.finish_and_load(TM_ACC1, w1);
             fold_pe_tc(T, w1);
             __syncthreads();
+            T.mark();                                                            // [trace] sweeps done
 
             // ================================================================================ x_bar -> outputs
             if (MODE == 1) {

@@ -18,6 +18,7 @@ struct Tile {
     int S;                  // samples per ray (mode 0)
     int rays_per_tile;      // M_TILE / S
     float beta;
+    __device__ __forceinline__ void mark() const {}      // trace hook of the tensor-core tile type (render_ray.cuh is generic)
 
     __device__ __forceinline__ float* pv(int v) const { return pt + v * M_TILE; }
 };
