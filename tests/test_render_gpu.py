@@ -325,3 +325,45 @@ def test_fused_eikonal_points_match_torch_restatement():
         res.append((pts.detach(), loc.grad, dirs.grad, sd.grad))
     for name, a, b in zip(("points", "cam_loc.grad", "ray_dirs.grad", "scale_dist.grad"), res[0], res[1]):
         _close(a, b, name, 2e-6)
+
+
+@pytest.mark.parametrize("S", [16, 32])
+def test_other_sample_counts_forward_and_backward_vs_oracle(S):
+    """render.n_samples_uniform = 16 / 32 (several rays per 128-point tile, segmented scans inside one warp): forward outputs and
+    a few gradients against the oracle's CPU autograd. Tolerances as in smoke(): outputs 1e-4, gradients 2e-3 of the largest entry."""
+    from shapeclipper_b200 import options
+    from shapeclipper_b200.implicit import SDFNetwork, RGBNetwork
+    from shapeclipper_b200.renderer import Renderer
+    torch.manual_seed(17)
+    opt = options.default_options(H=24, W=24)
+    opt.render.n_samples_uniform = S
+    sdf, rgb = SDFNetwork(opt), RGBNetwork(opt)
+    with torch.no_grad():
+        for p in sdf.parameters():
+            p.add_(0.02 * torch.randn_like(p))
+    ren = Renderer(opt, sdf, rgb)
+    B, Rn = 2, 40
+    th = torch.rand(B) * 6.28
+    Rm = torch.stack([torch.stack([-th.cos(), -th.sin(), torch.zeros(B)], -1),
+                      torch.stack([torch.zeros(B), torch.zeros(B), -torch.ones(B)], -1),
+                      torch.stack([th.sin(), -th.cos(), torch.zeros(B)], -1)], 1)
+    pose = torch.cat([Rm, torch.tensor([[0., 0., 5.]]).expand(B, 3)[..., None]], -1)
+    intr = torch.tensor([[96., 0, 12], [0, 96., 12], [0, 0, 1]]).repeat(B, 1, 1)
+    sd = torch.ones(B)
+    zs, zr = torch.randn(B, 64) * 0.3, torch.randn(B, 64) * 0.3
+    ridx = torch.stack([torch.randperm(24 * 24)[:Rn] for _ in range(B)])
+    sp = {k: v.detach().clone().requires_grad_(True) for k, v in sdf.state_dict().items()}
+    rp = {k: v.detach().clone().requires_grad_(True) for k, v in rgb.state_dict().items()}
+    cfg = R.RenderCfg(n_samples=S)
+    torch.manual_seed(1)
+    want = R.render(sp, rp, ren.density.beta.detach(), pose, intr, sd, zs, zr, 24, 24, ray_idx=ridx, training=True, cfg=cfg)
+    (want["rgb"].sum() + want["mask"].sum() + 0.1 * want["depth"].sum() + want["grad_eik"].sum()).backward()
+    ren = ren.cuda()
+    torch.manual_seed(1)
+    got = ren(opt, pose.cuda(), intr.cuda(), sd.cuda(), zs.cuda(), zr.cuda(), ray_idx=ridx.cuda(), training=True)
+    (got[0].sum() + got[1].sum() + 0.1 * got[3].sum() + got[5].sum()).backward()
+    for name, gt in (("rgb", got[0]), ("mask", got[1]), ("depth", got[3]), ("grad_eik", got[5])):
+        _close(gt, want[name].detach().view_as(gt.cpu()), name)
+    for k in ("lin0.weight", "lin3.weight", "lin5.weight", "lin2.bias"):
+        _grad_close(dict(sdf.named_parameters())[k].grad, sp[k].grad, "sdf." + k, 2e-3)
+    _grad_close(dict(rgb.named_parameters())["lin1.weight"].grad, rp["lin1.weight"].grad, "rgb.lin1.weight", 2e-3)
