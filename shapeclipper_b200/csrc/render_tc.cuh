@@ -201,6 +201,11 @@ __device__ __forceinline__ uint64_t desc_mn128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
+// low / high 32-bit words of those descriptors (start address field + LBO | SBO, version, swizzle)
+constexpr uint32_t kDescHi = 0x40004040u;
+__device__ __forceinline__ uint32_t desc_lo_k128(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_mn128(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((1024u >> 4) << 16); }
+
 #ifdef SC_TC_NOINLINE_ISSUE          // the backward kernel (the forward kernel's loops keep its issue code cache-resident: inline is faster there)
 #define SC_TC_ISSUE_FN static __device__ __noinline__
 #else
@@ -211,33 +216,101 @@ __device__ __forceinline__ uint64_t desc_mn128(uint32_t saddr) {
 // SASS instructions (25 % of the kernel) that the issuing warp walked once per tile, every line an instruction-cache miss
 // on the critical path of the phase (ncu: 29 % of the warp samples stalled on instruction fetch).
 SC_TC_ISSUE_FN void issue_layer_gemm(uint32_t tmem_d, const uint8_t* act, const uint8_t* w, bool accumulate) {
+    // ONE asm block for the 12 MMAs: descriptor low words are base + constant (the high word 0x40004040 = SBO 1024 B, version 1,
+    // SWIZZLE_128B never changes), the instruction descriptor and the elected-lane predicate are set up once. Issued as 12
+    // separate asm statements every MMA re-materialised its idesc and 64-bit descriptors in the (slow, scalar) uniform datapath:
+    // ~70 cycles per MMA against 32 cycles of tensor-pipe time (clock64 trace: 840 cycles of issue per layer GEMM).
     constexpr uint32_t idesc = sctc::make_idesc_bf16(128, 64);
     const uint32_t d = uniform_u32(tmem_d), acc = uniform_u32(accumulate ? 1u : 0u);
     const uint32_t a0 = uniform_u32(sctc::smem_u32(act)), w0 = uniform_u32(sctc::smem_u32(w));
-    const uint64_t ah = desc_k128(a0), al = desc_k128(a0 + kPlaneBytes);
-    const uint64_t wh = desc_k128(w0), wl = desc_k128(w0 + kWPlaneBytes);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint64_t adv = (uint64_t)(2 * k);
-        umma_bf16_elect(d, ah + adv, wh + adv, idesc, k > 0 ? 1u : acc);
-        umma_bf16_elect(d, ah + adv, wl + adv, idesc, 1u);
-        umma_bf16_elect(d, al + adv, wh + adv, idesc, 1u);
-    }
+    const uint32_t ah = desc_lo_k128(a0), al = desc_lo_k128(a0 + kPlaneBytes), wh = desc_lo_k128(w0), wl = desc_lo_k128(w0 + kWPlaneBytes);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q, t;\n\t"
+        ".reg .b32 xa, xb, ya, yb;\n\t"
+        ".reg .b64 da, db, ea, eb;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.u32 t, %5, %5;\n\t"
+        "add.u32 xa, %1, 0; add.u32 xb, %2, 0; add.u32 ya, %3, 0; add.u32 yb, %4, 0;\n\t"
+        "mov.b64 da, {xa, %6}; mov.b64 db, {xb, %6}; mov.b64 ea, {ya, %6}; mov.b64 eb, {yb, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %7, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, eb, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], db, ea, %7, t;\n\t"
+        "add.u32 xa, %1, 2; add.u32 xb, %2, 2; add.u32 ya, %3, 2; add.u32 yb, %4, 2;\n\t"
+        "mov.b64 da, {xa, %6}; mov.b64 db, {xb, %6}; mov.b64 ea, {ya, %6}; mov.b64 eb, {yb, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, eb, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], db, ea, %7, t;\n\t"
+        "add.u32 xa, %1, 4; add.u32 xb, %2, 4; add.u32 ya, %3, 4; add.u32 yb, %4, 4;\n\t"
+        "mov.b64 da, {xa, %6}; mov.b64 db, {xb, %6}; mov.b64 ea, {ya, %6}; mov.b64 eb, {yb, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, eb, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], db, ea, %7, t;\n\t"
+        "add.u32 xa, %1, 6; add.u32 xb, %2, 6; add.u32 ya, %3, 6; add.u32 yb, %4, 6;\n\t"
+        "mov.b64 da, {xa, %6}; mov.b64 db, {xb, %6}; mov.b64 ea, {ya, %6}; mov.b64 eb, {yb, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, eb, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], db, ea, %7, t;\n\t"
+        "}"
+        ::"r"(d), "r"(ah), "r"(al), "r"(wh), "r"(wl), "r"(acc), "r"(kDescHi), "r"(idesc) : "memory");
 }
-// D[64 x 64] += L^T . R over the tile's 128 points (L, R = plane pairs). Called by the whole issuing warp.
+// D[64 x 64] += L^T . R over the tile's 128 points (L, R = plane pairs). Called by the whole issuing warp. 24 MMAs, one asm block.
 SC_TC_ISSUE_FN void issue_wgrad(uint32_t tmem_d, const uint8_t* L, const uint8_t* R, bool accumulate) {
     constexpr uint32_t idesc = make_idesc_bf16_mn(64, 64);
     const uint32_t d = uniform_u32(tmem_d), acc = uniform_u32(accumulate ? 1u : 0u);
     const uint32_t l0 = uniform_u32(sctc::smem_u32(L)), r0 = uniform_u32(sctc::smem_u32(R));
-    const uint64_t lh = desc_mn128(l0), ll = desc_mn128(l0 + kPlaneBytes);
-    const uint64_t rh = desc_mn128(r0), rl = desc_mn128(r0 + kPlaneBytes);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint64_t adv = (uint64_t)(k * (16 * 128 >> 4));          // 16 points = 16 rows of 128 B
-        umma_bf16_elect(d, lh + adv, rh + adv, idesc, k > 0 ? 1u : acc);
-        umma_bf16_elect(d, lh + adv, rl + adv, idesc, 1u);
-        umma_bf16_elect(d, ll + adv, rh + adv, idesc, 1u);
-    }
+    const uint32_t lh = desc_lo_mn128(l0), ll = desc_lo_mn128(l0 + kPlaneBytes), rh = desc_lo_mn128(r0), rl = desc_lo_mn128(r0 + kPlaneBytes);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q, t;\n\t"
+        ".reg .b32 xa, xb, ya, yb;\n\t"
+        ".reg .b64 da, db, ea, eb;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "setp.eq.u32 t, %5, %5;\n\t"
+        "add.u32 xa, %1, 0; add.u32 xb, %2, 0; add.u32 ya, %3, 0; add.u32 yb, %4, 0;\n\t"
+        "mov.b64 da, {xa, %6}; mov.b64 db, {xb, %6}; mov.b64 ea, {ya, %6}; mov.b64 eb, {yb, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %7, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, eb, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], db, ea, %7, t;\n\t"
+        "add.u32 xa, %1, 128; add.u32 xb, %2, 128; add.u32 ya, %3, 128; add.u32 yb, %4, 128;\n\t"
+        "mov.b64 da, {xa, %6}; mov.b64 db, {xb, %6}; mov.b64 ea, {ya, %6}; mov.b64 eb, {yb, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, eb, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], db, ea, %7, t;\n\t"
+        "add.u32 xa, %1, 256; add.u32 xb, %2, 256; add.u32 ya, %3, 256; add.u32 yb, %4, 256;\n\t"
+        "mov.b64 da, {xa, %6}; mov.b64 db, {xb, %6}; mov.b64 ea, {ya, %6}; mov.b64 eb, {yb, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, eb, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], db, ea, %7, t;\n\t"
+        "add.u32 xa, %1, 384; add.u32 xb, %2, 384; add.u32 ya, %3, 384; add.u32 yb, %4, 384;\n\t"
+        "mov.b64 da, {xa, %6}; mov.b64 db, {xb, %6}; mov.b64 ea, {ya, %6}; mov.b64 eb, {yb, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, eb, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], db, ea, %7, t;\n\t"
+        "add.u32 xa, %1, 512; add.u32 xb, %2, 512; add.u32 ya, %3, 512; add.u32 yb, %4, 512;\n\t"
+        "mov.b64 da, {xa, %6}; mov.b64 db, {xb, %6}; mov.b64 ea, {ya, %6}; mov.b64 eb, {yb, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, eb, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], db, ea, %7, t;\n\t"
+        "add.u32 xa, %1, 640; add.u32 xb, %2, 640; add.u32 ya, %3, 640; add.u32 yb, %4, 640;\n\t"
+        "mov.b64 da, {xa, %6}; mov.b64 db, {xb, %6}; mov.b64 ea, {ya, %6}; mov.b64 eb, {yb, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, eb, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], db, ea, %7, t;\n\t"
+        "add.u32 xa, %1, 768; add.u32 xb, %2, 768; add.u32 ya, %3, 768; add.u32 yb, %4, 768;\n\t"
+        "mov.b64 da, {xa, %6}; mov.b64 db, {xb, %6}; mov.b64 ea, {ya, %6}; mov.b64 eb, {yb, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, eb, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], db, ea, %7, t;\n\t"
+        "add.u32 xa, %1, 896; add.u32 xb, %2, 896; add.u32 ya, %3, 896; add.u32 yb, %4, 896;\n\t"
+        "mov.b64 da, {xa, %6}; mov.b64 db, {xb, %6}; mov.b64 ea, {ya, %6}; mov.b64 eb, {yb, %6};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, eb, %7, t;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], db, ea, %7, t;\n\t"
+        "}"
+        ::"r"(d), "r"(lh), "r"(ll), "r"(rh), "r"(rl), "r"(acc), "r"(kDescHi), "r"(idesc) : "memory");
 }
 
 // ---- weight ring: NS slots, TMA-filled (wfull), released by tcgen05.commit (wfree). Prefetch distance NS - 1:
