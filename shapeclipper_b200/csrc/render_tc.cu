@@ -80,6 +80,7 @@ __device__ __forceinline__ void tc_init_tile_struct(TileTC& T, uint8_t* smem, co
     T.tid = threadIdx.x; T.lane = threadIdx.x & 31; T.warp = threadIdx.x >> 5;
     T.w0 = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0;          // warp-uniform for the compiler too
     T.wr.w0 = T.w0;
+    T.wide = true;
     T.row = 32 * (T.warp & 3) + T.lane; T.ch = T.warp >> 2;
 }
 

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
         T.tid = threadIdx.x; T.lane = threadIdx.x & 31; T.warp = threadIdx.x >> 5;
         T.w0 = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0;      // the issuing warp, warp-uniform for the compiler too
         T.wr.w0 = T.w0;
+        T.wide = false;            // TMEM is full here (12 weight-gradient accumulators)
         T.row = 32 * (T.warp & 3) + T.lane; T.ch = T.warp >> 2;
 #ifdef SC_TC_TRACE
         T.trace = (MODE == 0) ? reinterpret_cast<long long*>(a.points_bar) : nullptr; T.trace_n = 0;

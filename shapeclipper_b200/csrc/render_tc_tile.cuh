@@ -16,6 +16,7 @@ struct TileTC {
     uint32_t tmem;
     int tid, lane, warp, row, ch;
     bool w0;                    // member of the issuing warp (warp 0, warp-uniform)
+    bool wide;                  // forward kernel: 128-column accumulators (issue_layer_gemm_wide); accumulator a lives at columns 2 a
     int b, first, S, rays_per_tile;
     float beta;
 #ifdef SC_TC_TRACE
@@ -42,7 +43,16 @@ struct TileTC {
         mark();
         mma_phase ^= 1;
         sctc::tc_fence_after();
-        tmem_ld_32x16(tmem + acc_col + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(NC * ch), v);
+        if (wide) {
+            float u[NC];
+            const uint32_t base = tmem + 2 * acc_col + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(NC * ch);
+            tmem_ld_32x16(base, v);
+            tmem_ld_32x16(base + 64, u);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) v[i] += u[i];
+        } else {
+            tmem_ld_32x16(tmem + acc_col + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(NC * ch), v);
+        }
         mark();
     }
     // one layer GEMM: acquire weights, (thread 0) issue + release
@@ -50,7 +60,11 @@ struct TileTC {
         mark();
         const uint8_t* w = wr.acquire();
         mark();
-        if (w0) { issue_layer_gemm(tmem + acc_col, a, w, accumulate); wr.release(); }
+        if (w0) {
+            if (wide) issue_layer_gemm_wide(tmem + 2 * acc_col, a, w, accumulate);
+            else issue_layer_gemm(tmem + acc_col, a, w, accumulate);
+            wr.release();
+        }
     }
 };
 
