@@ -29,8 +29,8 @@ UNIT = "images/s"
 FLOP_FWD_PER_POINT = 199424.0       # SURVEY.md §8d convention: 2*(40320 SDF + 40320 grad-SDF + 19072 RGB)
 FLOP_BWD_PER_POINT = 398848.0       # train fwd+bwd = 3x fwd  ->  backward kernel = 2x fwd
 GRAPH_PARAMS = 36800589             # parameters of the reference Graph (flat all-reduce size)
-RENDER_BWD_DRAM_BYTES = 2467901000  # dram__bytes_read.sum + dram__bytes_write.sum of one render_tc_bwd_kernel<0> launch at this shape
-                                    # (ncu --set full, profiles/r01e_render_tc_bwd_ncu_summary.txt: 1.93 GB of saved activations read)
+RENDER_BWD_DRAM_BYTES = 2462139000  # dram__bytes_read.sum + dram__bytes_write.sum of one render_tc_bwd_kernel<0> launch at this shape
+                                    # (ncu --set full, profiles/r01h_render_tc_bwd_ncu_summary.txt: 1.93 GB of saved activations read)
 
 
 def parse():
