@@ -100,24 +100,6 @@ __device__ __forceinline__ void row_store(uint8_t* act, int r, int ch, const flo
         *reinterpret_cast<uint4*>(lo + pos) = l;
     }
 }
-// read them back (hi + lo, ~2^-17 relative)
-__device__ __forceinline__ void row_load(const uint8_t* act, int r, int ch, float (&v)[NC]) {
-    const uint8_t* hi = act + r * 128;
-    const uint8_t* lo = hi + kPlaneBytes;
-#pragma unroll
-    for (int q = 0; q < NC / 8; ++q) {
-        const int pos = ((ch * (NC / 8) + q) ^ (r & 7)) << 4;
-        const uint4 h = *reinterpret_cast<const uint4*>(hi + pos);
-        const uint4 l = *reinterpret_cast<const uint4*>(lo + pos);
-        const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&h);
-        const __nv_bfloat162* lp = reinterpret_cast<const __nv_bfloat162*>(&l);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float2 a = __bfloat1622float2(hp[e]), b = __bfloat1622float2(lp[e]);
-            v[q * 8 + 2 * e] = a.x + b.x; v[q * 8 + 2 * e + 1] = a.y + b.y;
-        }
-    }
-}
 // single element (row r, column c) of a plane pair
 __device__ __forceinline__ float act_elem(const uint8_t* act, int r, int c) {
     const int off = r * 128 + ((((c >> 3) ^ (r & 7))) << 4) + ((c & 7) << 1);
@@ -178,14 +160,6 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\tselp.u32 %0, 1, 0, q;\n\t}" : "=r"(p));
     return p != 0;
 }
-__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\t"
-        "elect.sync _|q, 0xffffffff;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\t"
@@ -193,15 +167,8 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
         "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
         ::"r"(sctc::smem_u32(bar)) : "memory");
 }
-// K-major / MN-major descriptors from a (warp-uniform) shared-memory byte address
-__device__ __forceinline__ uint64_t desc_k128(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ uint64_t desc_mn128(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-
-// low / high 32-bit words of those descriptors (start address field + LBO | SBO, version, swizzle)
+// low / high 32-bit words of the K-major / MN-major shared-memory descriptors of a (warp-uniform) byte address
+// (start address field + LBO | SBO, version, swizzle)
 constexpr uint32_t kDescHi = 0x40004040u;
 __device__ __forceinline__ uint32_t desc_lo_k128(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 __device__ __forceinline__ uint32_t desc_lo_mn128(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((1024u >> 4) << 16); }

@@ -75,13 +75,6 @@ constexpr int TS_H = 0, TS_Q = 5, TS_FEAT = 9, TS_R = 10, TS_GPE = 13, TS_FB = 1
 constexpr int TS_SAVED_PV = 14, TS_SAVED_PLANES = 15;
 constexpr int kSavedVecs = 13;
 // forward (store = true): per-point vectors the backward needs -> plane TS_SAVED_PV of the tile's saved block; backward: back.
-// backward, split in two so that the HBM latency of the loads overlaps the tile set-up: issue the loads into registers ...
-__device__ __forceinline__ void saved_vectors_prefetch(const TileTC& T, const float* plane, float (&reg)[13]) {
-    if (T.tid < M_TILE) {
-#pragma unroll
-        for (int i = 0; i < 13; ++i) reg[i] = __ldcg(plane + i * M_TILE + T.tid);
-    }
-}
 template <bool STORE>
 __device__ __forceinline__ void saved_vectors(const TileTC& T, float* plane) {
     constexpr int vecs[kSavedVecs] = {scr::PV_SDF, scr::PV_COL0, scr::PV_COL1, scr::PV_COL2, scr::PV_GX0, scr::PV_GX1, scr::PV_GX2,
@@ -94,29 +87,6 @@ __device__ __forceinline__ void saved_vectors(const TileTC& T, float* plane) {
         }
     }
 }
-// ... and publish them to the per-point vectors afterwards
-__device__ __forceinline__ void saved_vectors_commit(const TileTC& T, const float (&reg)[13]) {
-    constexpr int vecs[kSavedVecs] = {scr::PV_SDF, scr::PV_COL0, scr::PV_COL1, scr::PV_COL2, scr::PV_GX0, scr::PV_GX1, scr::PV_GX2,
-                                      scr::PV_SIG, scr::PV_CF, scr::PV_UN, scr::PV_NS0, scr::PV_NS1, scr::PV_NS2};
-    if (T.tid < M_TILE) {
-#pragma unroll
-        for (int i = 0; i < kSavedVecs; ++i) T.pv(vecs[i])[T.tid] = reg[i];
-    }
-}
-
-// d pe_k / d x~ for feature k of point p, from the posenc plane pair
-__device__ __forceinline__ float dpe_tc(const uint8_t* P, int k, int p) {
-    if (k < 3) return 1.f;
-    const int f = (k - 3) / 6, r = (k - 3) % 6;
-    const float fr = (float)(1 << f);
-    return (r < 3) ? fr * act_elem(P, p, k + 3) : -fr * act_elem(P, p, k - 3);
-}
-__device__ __forceinline__ float d2pe_tc(const uint8_t* P, int k, int p) {
-    if (k < 3) return 0.f;
-    const float fr = (float)(1 << ((k - 3) / 6));
-    return -fr * fr * act_elem(P, p, k);
-}
-
 // ---- posenc derivatives of one row for the 16 columns of column group CH, with compile-time column roles.
 // d pe_k / d x~ = +-2^f pe_partner(k) (sin <-> cos, 3 columns away), d2 pe_k / d x~2 = -4^f pe_k. The row's posenc values are read
 // back from the operand plane with four 16-byte loads per plane (columns 16 CH - 8 .. 16 CH + 23, conflict-free) instead of
