@@ -59,5 +59,44 @@ def load():
     return mod
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's Python modules as SOURCELESS bytecode: oracle/_ref/py/{model,utils,data}/*.pyc + CLIP_anno.pyc, compiled
+# by py_compile straight from /root/reference (nothing is copied as source; oracle/_ref is git-ignored and, like the .so
+# above, travels to the GPU box with the gpurun snapshot). tests/test_dropin_gpu.py imports them there to run the
+# reference's OWN Graph / eval_3D / NN_annotator unshimmed on the CPU and shimmed on the GPU. The option tree is staged as
+# data (YAML -> JSON).
+PY_OUT = os.path.join(OUT, "py")
+PY_TREES = ("model", "utils", "data")
+PY_FILES = ("CLIP_anno.py",)
+
+
+def stage_python(force=False):
+    import json
+    import py_compile
+    if not os.path.isdir(os.path.join(REF, "model")):
+        return PY_OUT if os.path.isdir(PY_OUT) else None
+    n = 0
+    todo = [(t, f) for t in PY_TREES for f in sorted(os.listdir(os.path.join(REF, t))) if f.endswith(".py")]
+    todo += [("", f) for f in PY_FILES]
+    for sub, f in todo:
+        src = os.path.join(REF, sub, f)
+        dst = os.path.join(PY_OUT, sub, f + "c")
+        if os.path.isfile(dst) and not force and os.path.getmtime(dst) >= os.path.getmtime(src):
+            continue
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        py_compile.compile(src, cfile=dst, dfile="<reference>/" + os.path.join(sub, f), doraise=True,
+                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+        n += 1
+    import yaml
+    for rel in (("options", "pix3d", "config.yaml"), ("options", "clip", "pix3d.yaml")):
+        src = os.path.join(REF, *rel)
+        dst = os.path.join(PY_OUT, *rel)[:-5] + ".json"
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        with open(src) as fi, open(dst, "w") as fo:
+            json.dump(yaml.safe_load(fi), fo)
+    return PY_OUT
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(stage_python(force="--force" in sys.argv))

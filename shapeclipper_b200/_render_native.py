@@ -186,7 +186,15 @@ def saved_buffer(device, batch, n_per_image, n_samples):
     n = L.sc_render_tc_saved_bytes(int(batch), int(n_per_image), int(n_samples))
     if n == 0 or n > SAVE_ACTIVATIONS_MAX_BYTES:
         return None
-    return torch.empty(n // 4, dtype=torch.float32, device=device)
+    # several renders' buffers are alive at once (1 + n_views per step): leave half of what is free right now alone
+    free, _ = torch.cuda.mem_get_info(device)
+    reusable = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    if n > (free + reusable) // 2:
+        return None
+    try:
+        return torch.empty(n // 4, dtype=torch.float32, device=device)
+    except torch.cuda.OutOfMemoryError:
+        return None                                    # the backward recomputes the forward per tile instead
 
 
 class KernelTimers:

@@ -34,7 +34,8 @@ class HotPathGraph(nn.Module):
         (var.rgb_recon, var.mask_recon, var.mask_hard, var.depth_recon, var.normal_recon, var.grad_eikonal) = \
             self.renderer(opt, var.pose, var.intr, var.scale_dist, var.proj_latent_sdf, var.proj_latent_rgb,
                           ray_idx=ray_idx, training=training)
-        if training and (opt.loss_weight.nearest_img is not None or opt.loss_weight.nearest_mask is not None):
+        lw = opt.loss_weight
+        if training and (lw.nearest_img is not None or lw.nearest_mask is not None):      # model/graph.py:104
             self.forward_NN(opt, var, training=training)
         if get_loss:
             return var, self.compute_loss(opt, var, training)
@@ -88,8 +89,10 @@ class HotPathGraph(nn.Module):
     # ------------------------------------------------------------------------------------------------------
     def compute_loss(self, opt, var, training=False):
         lw, fns = opt.loss_weight, self.loss_fns
+        nn_w = (lw.nearest_img, lw.nearest_mask, lw.nearest_normal)
         fused = (var.rgb_recon.is_cuda and fns.mask_mse == 0. and lw.render is not None and lw.mask is not None
-                 and lw.normal is not None and getattr(opt.reg, "fused_losses", True))
+                 and lw.normal is not None and getattr(opt.reg, "fused_losses", True)
+                 and (all(w is not None for w in nn_w) or all(w is None for w in nn_w)))    # the fused kernel computes all three
         if fused:
             return self._compute_loss_fused(opt, var, training)
         L = {}
@@ -102,13 +105,23 @@ class HotPathGraph(nn.Module):
             L["normal"] = fns.normal_loss(var.normal_recon, var.normal_transformed, valid, tolerance=opt.reg.normal_tol)
         if lw.eikonal is not None and training:
             L["eikonal"] = fns.MSE_loss(var.grad_eikonal.view(var.rgb_recon.shape[0], -1), 1)
-        if training and lw.nearest_img is not None:
-            L["nearest_img"], L["nearest_mask"], L["nearest_normal"] = 0, 0, 0
+        # each neighbour loss is gated on its OWN weight, as in the reference (model/graph.py:241-263)
+        rendered_nn = training and ("rgb_recon_NN_0" in var)
+        if rendered_nn and lw.nearest_img is not None:
+            L["nearest_img"] = 0
+            for v in range(opt.reg.n_views):
+                tag = "NN_%d" % v
+                L["nearest_img"] = L["nearest_img"] + fns.MSE_loss(var["rgb_recon_" + tag], var["input_" + tag]["rgb_input"])
+        if rendered_nn and lw.nearest_mask is not None:
+            L["nearest_mask"] = 0
+            for v in range(opt.reg.n_views):
+                tag = "NN_%d" % v
+                L["nearest_mask"] = L["nearest_mask"] + fns.mask_loss(var["mask_recon_" + tag], var["input_" + tag]["mask_input"])
+        if rendered_nn and lw.nearest_normal is not None:
+            L["nearest_normal"] = 0
             for v in range(opt.reg.n_views):
                 tag = "NN_%d" % v
                 inp = var["input_" + tag]
-                L["nearest_img"] = L["nearest_img"] + fns.MSE_loss(var["rgb_recon_" + tag], inp["rgb_input"])
-                L["nearest_mask"] = L["nearest_mask"] + fns.mask_loss(var["mask_recon_" + tag], inp["mask_input"])
                 valid = (inp["mask_input"] > 0.5) & (var["mask_recon_" + tag] > 0.5)
                 target = inp["normal_input"] @ var["pose_" + tag][..., :3]
                 L["nearest_normal"] = L["nearest_normal"] + fns.normal_loss(var["normal_recon_" + tag], target, valid,

@@ -119,5 +119,8 @@ class TrainStep:
         self._g_main.replay()
         self.flat.all_reduce()
         self._g_optim.replay()
+        # a replayed optimiser step rewrites the weights without bumping their version counters: packed weight blobs cached
+        # by eager callers (validation renders, eval_3D.compute_level_grid) would otherwise stay at the first call's weights
+        rn.invalidate_blob_cache()
         rn.TIMERS.count(self.launches_per_step)
         return self.loss

@@ -157,9 +157,104 @@ def case_losses(mods, name, seed):
     print("wrote", name, {k: float(v) for k, v in out.items()})
 
 
+def reference_forward_NN_choice(mods, opt, var):
+    """Runs the reference's Graph.forward_NN (model/graph.py:114-218) with the CNNs / renderer of `self` replaced by dummies
+    and returns the neighbour it selected per sample (model/graph.py:119-142: IoU -> (1-IoU)^T -> np.random.choice)."""
+    import types
+    B = var.mask_input.shape[0]
+    z6 = tuple(torch.zeros(B, 1) for _ in range(6))
+    fake = types.SimpleNamespace(encoder=lambda x: torch.zeros(B, opt.arch.latent_dim_shape + opt.arch.latent_dim_rgb),
+                                 latent_proj_rgb=lambda x: x[:, :64],
+                                 pred_pose=lambda *a, **k: (torch.zeros(B, 3, 4), torch.zeros(B, 3, 3), torch.ones(B)),
+                                 renderer=lambda *a, **k: z6)
+    mods.graph.Graph.forward_NN(fake, opt, var)
+    return torch.stack([var["input_NN_%d" % v].ray_idx[:, 0] for v in range(opt.reg.n_views)], dim=1)   # ray_idx_NN[b,:,k] == k
+
+
+def neighbour_var(mods, opt, B, R, seed):
+    g = torch.Generator().manual_seed(seed)
+    K = opt.data.k_nearest
+    v = mods.util.EasyDict()
+    v.idx = torch.arange(B)
+    q = (torch.rand(B, R, 1, generator=g) > 0.5).float()
+    flip = torch.rand(B, R, 1, K, generator=g) < torch.linspace(0.25, 0.45, K).view(1, 1, 1, K)      # IoU spread over the K neighbours
+    v.mask_input = q
+    v.mask_input_NN = torch.where(flip, 1 - q.unsqueeze(-1), q.unsqueeze(-1)).contiguous()
+    v.rgb_input, v.normal_input = torch.zeros(B, R, 3), torch.zeros(B, R, 3)
+    v.rgb_input_NN, v.normal_input_NN = torch.zeros(B, R, 3, K), torch.zeros(B, R, 3, K)
+    v.rgb_input_map, v.mask_input_map, v.normal_input_map = torch.zeros(B, 3, 2, 2), torch.zeros(B, 1, 2, 2), torch.zeros(B, 3, 2, 2)
+    v.rgb_input_map_NN, v.mask_input_map_NN = torch.zeros(B, 3, 2, 2, K), torch.zeros(B, 1, 2, 2, K)
+    v.normal_input_map_NN = torch.zeros(B, 3, 2, 2, K)
+    v.pose_gt, v.pose_gt_NN = torch.zeros(B, 3, 4), torch.zeros(B, 3, 4, K)
+    v.ray_idx = torch.zeros(B, R, dtype=torch.long)
+    v.ray_idx_NN = torch.arange(K).view(1, 1, K).expand(B, R, K).contiguous()
+    v.proj_latent_sdf = torch.zeros(B, 64)
+    return v
+
+
+def case_neighbours(mods, name, seed):
+    import numpy as np
+    gm = rh.import_reference_graph()
+    out = {}
+    for n_views in (1, 2):
+        opt = rh.load_reference_opt(H=2, W=2)
+        opt.reg.n_views = n_views
+        var = neighbour_var(gm, opt, 16, 96, seed)
+        np.random.seed(seed)
+        choice = reference_forward_NN_choice(gm, opt, var)
+        out["views%d" % n_views] = dict(mask_input=var.mask_input.clone(), mask_input_NN=var.mask_input_NN.clone(), np_seed=seed,
+                                       choice=choice.clone(), sample_temp=opt.reg.sample_temp)
+    torch.save(out, os.path.join(OUT, name + ".pt"))
+    print("wrote", name, out["views1"]["choice"].flatten().tolist())
+
+
+def case_eval3d(mods, name, seed):
+    """utils/eval_3D.py normalize_pc (40-49) and compute_fscore (105-121, incl. the NaN -> 0 rule) of the reference."""
+    import importlib
+    ev = importlib.import_module("utils.eval_3D")
+    g = torch.Generator().manual_seed(seed)
+    pc = torch.randn(3, 500, 3, generator=g) * torch.tensor([0.3, 0.5, 0.2]) + torch.tensor([0.1, -0.2, 0.05])
+    d1 = torch.rand(4, 700, generator=g) * 0.15
+    d2 = torch.rand(4, 650, generator=g) * 0.25
+    d1[3] += 1.0
+    d2[3] += 1.0                              # nothing under any threshold: precision + recall = 0 -> NaN -> 0
+    th = [0.005, 0.01, 0.02, 0.05, 0.1, 0.2]
+    torch.save(dict(pc=pc, pc_normalized=ev.normalize_pc(pc), dist1=d1, dist2=d2, thresholds=th,
+                    fscore=ev.compute_fscore(d1, d2, th)), os.path.join(OUT, name + ".pt"))
+    print("wrote", name)
+
+
+def case_calc_matches(mods, name, seed):
+    """NN_annotator.calc_matches (CLIP_anno.py:29-57) of the reference: top-k branch and the opt.thres sampling branch (its
+    torch.randperm draws come from the CPU generator, seeded here). `clip` is absent: stubbed, never called."""
+    import importlib
+    rh._stub("clip")
+    anno = importlib.import_module("CLIP_anno")
+    ann = anno.NN_annotator.__new__(anno.NN_annotator)
+    g = torch.Generator().manual_seed(seed)
+    centres = torch.randn(6, 64, generator=g)
+    feats = torch.nn.functional.normalize(centres[torch.arange(90) % 6] + 0.35 * torch.randn(90, 64, generator=g), dim=-1)
+    out = dict(features=feats)
+    opt = mods.util.EasyDict(thres=None, device="cpu")
+    ind, val = ann.calc_matches(opt, feats, k_nearest=6)
+    out["topk"] = dict(indices=torch.stack(ind), values=val)
+    for thres in (0.55, 0.89):
+        opt = mods.util.EasyDict(thres=thres, device="cpu")
+        torch.manual_seed(seed)
+        ind, val = ann.calc_matches(opt, feats, k_nearest=6)
+        out["thres_%g" % thres] = dict(indices=torch.stack(ind), values=val, seed=seed, thres=thres)
+    torch.save(out, os.path.join(OUT, name + ".pt"))
+    print("wrote", name)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     mods = rh.import_reference()
+    if "--round2" in sys.argv:
+        case_neighbours(mods, "neighbours", seed=8)
+        case_eval3d(mods, "eval3d", seed=9)
+        case_calc_matches(mods, "calc_matches", seed=10)
+        return
     if "--only-visualize" in sys.argv:
         case_visualize(mods, "render_visualize_10x10", 10, 10, 2, seed=6)
         return
@@ -169,6 +264,9 @@ def main():
     case_render(mods, "render_train_full_8x8", 8, 8, 1, None, True, seed=3)
     case_sdf_query(mods, "sdf_query", seed=4)
     case_losses(mods, "losses", seed=5)
+    case_neighbours(mods, "neighbours", seed=8)
+    case_eval3d(mods, "eval3d", seed=9)
+    case_calc_matches(mods, "calc_matches", seed=10)
 
 
 if __name__ == "__main__":

@@ -11,10 +11,20 @@ import os
 import sys
 import types
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ROOT = os.path.join(os.path.dirname(_HERE), "oracle", "_ref", "py")   # sourceless .pyc, see oracle/build_ref.py
 REF_ROOT = os.environ.get("SC_REFERENCE_ROOT", "/root/reference")
+if not os.path.isfile(os.path.join(REF_ROOT, "model", "renderer.py")) and os.path.isfile(os.path.join(STAGED_ROOT, "model", "renderer.pyc")):
+    REF_ROOT = STAGED_ROOT                     # the GPU box: the bytecode build_ref.stage_python() compiled from the reference
 
 
 def reference_available():
+    return (os.path.isfile(os.path.join(REF_ROOT, "model", "renderer.py"))
+            or os.path.isfile(os.path.join(REF_ROOT, "model", "renderer.pyc")))
+
+
+def source_available():
+    """True only where the reference SOURCES are (the build container): tests that read reference text need this."""
     return os.path.isfile(os.path.join(REF_ROOT, "model", "renderer.py"))
 
 
@@ -55,10 +65,16 @@ def import_reference():
 
 def load_reference_opt(H=None, W=None, **overrides):
     """EasyDict options from the reference's own YAML (options/pix3d/config.yaml), CPU device."""
-    import yaml
     mods = import_reference()
-    with open(os.path.join(REF_ROOT, "options", "pix3d", "config.yaml")) as f:
-        opt = mods.util.EasyDict(yaml.safe_load(f))
+    y = os.path.join(REF_ROOT, "options", "pix3d", "config.yaml")
+    if os.path.isfile(y):
+        import yaml
+        with open(y) as f:
+            opt = mods.util.EasyDict(yaml.safe_load(f))
+    else:
+        import json
+        with open(y[:-5] + ".json") as f:
+            opt = mods.util.EasyDict(json.load(f))
     opt.device = "cpu"
     opt.H, opt.W = opt.image_size
     if H is not None:

@@ -115,3 +115,26 @@ def test_fused_render_losses_match_torch_losses():
     for k in base:
         ga, gb = res[0][1][k], res[1][1][k]
         assert float((ga - gb).abs().max()) <= 1e-6 * max(float(gb.abs().max()), 1e-6) + 1e-9, k
+
+
+def test_eager_render_sees_weights_updated_by_graph_replays():
+    """A replayed optimiser step rewrites the weights without bumping tensor versions: an eager render between replays must
+    not reuse a weight blob packed before them (TrainStep invalidates the pack cache after every replay)."""
+    from shapeclipper_b200 import _render_native as rn, eval_3D
+    step, params, batch = _make(True)
+    opt, g = step.opt, step.graph
+    pts = (torch.rand(1, 4000, 3, device="cuda") - 0.5)
+    z = torch.randn(1, 64, device="cuda") * 0.3
+
+    def level():
+        with torch.no_grad():
+            return g.sdf_network.get_conditional_output(opt, 1, pts.reshape(-1, 3), z, compute_grad=False)[0].clone()
+    before = level()
+    assert torch.equal(before, level())                    # cached blob, same weights: identical
+    step.load(batch)
+    for _ in range(3):
+        step()
+    after = level()
+    assert float((after - before).abs().max()) > 0, "eager SDF query still uses the weights from before the replays"
+    rn.invalidate_blob_cache()
+    assert torch.equal(after, level())                     # equals a render from freshly packed weights
