@@ -60,14 +60,15 @@ def load():
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# The reference's Python modules as SOURCELESS bytecode: oracle/_ref/py/{model,utils,data}/*.pyc + CLIP_anno.pyc, compiled
+# The reference's Python modules as SOURCELESS bytecode: oracle/_ref/py/{model,utils,data}/*.refbc + CLIP_anno.refbc, compiled
 # by py_compile straight from /root/reference (nothing is copied as source; oracle/_ref is git-ignored and, like the .so
-# above, travels to the GPU box with the gpurun snapshot). tests/test_dropin_gpu.py imports them there to run the
+# above, travels to the GPU box with the gpurun snapshot — which drops *.pyc, hence the suffix and the small importer below). tests/test_dropin_gpu.py imports them there to run the
 # reference's OWN Graph / eval_3D / NN_annotator unshimmed on the CPU and shimmed on the GPU. The option tree is staged as
 # data (YAML -> JSON).
 PY_OUT = os.path.join(OUT, "py")
 PY_TREES = ("model", "utils", "data")
 PY_FILES = ("CLIP_anno.py",)
+SUFFIX = ".refbc"
 
 
 def stage_python(force=False):
@@ -80,7 +81,7 @@ def stage_python(force=False):
     todo += [("", f) for f in PY_FILES]
     for sub, f in todo:
         src = os.path.join(REF, sub, f)
-        dst = os.path.join(PY_OUT, sub, f + "c")
+        dst = os.path.join(PY_OUT, sub, f[:-3] + SUFFIX)
         if os.path.isfile(dst) and not force and os.path.getmtime(dst) >= os.path.getmtime(src):
             continue
         os.makedirs(os.path.dirname(dst), exist_ok=True)
@@ -95,6 +96,47 @@ def stage_python(force=False):
         with open(src) as fi, open(dst, "w") as fo:
             json.dump(yaml.safe_load(fi), fo)
     return PY_OUT
+
+
+def staged_available():
+    return os.path.isfile(os.path.join(PY_OUT, "model", "renderer" + SUFFIX))
+
+
+def install_staged_importer():
+    """Makes `import model.graph`, `import utils.eval_3D`, `import CLIP_anno` ... resolve to the staged bytecode."""
+    import importlib.abc
+    import importlib.machinery
+    import marshal
+
+    class Loader(importlib.abc.Loader):
+        def __init__(self, path):
+            self.path = path
+
+        def create_module(self, spec):
+            return None
+
+        def exec_module(self, module):
+            with open(self.path, "rb") as f:
+                code = marshal.loads(f.read()[16:])            # 16-byte pyc header, then the code object
+            exec(code, module.__dict__)
+
+    class Finder(importlib.abc.MetaPathFinder):
+        def find_spec(self, fullname, path=None, target=None):
+            base = os.path.join(PY_OUT, *fullname.split("."))
+            if os.path.isfile(base + SUFFIX):
+                return importlib.machinery.ModuleSpec(fullname, Loader(base + SUFFIX), origin=base + SUFFIX)
+            if os.path.isdir(base) and fullname.split(".")[0] in PY_TREES:
+                init = os.path.join(base, "__init__" + SUFFIX)
+                spec = importlib.machinery.ModuleSpec(fullname, Loader(init) if os.path.isfile(init) else None,
+                                                      origin=base, is_package=True)
+                spec.submodule_search_locations = [base]
+                return spec
+            return None
+
+    if not any(type(f).__name__ == "Finder" and getattr(f, "_sc_staged", False) for f in sys.meta_path):
+        f = Finder()
+        f._sc_staged = True
+        sys.meta_path.insert(0, f)
 
 
 if __name__ == "__main__":

@@ -12,15 +12,15 @@ import sys
 import types
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-STAGED_ROOT = os.path.join(os.path.dirname(_HERE), "oracle", "_ref", "py")   # sourceless .pyc, see oracle/build_ref.py
+STAGED_ROOT = os.path.join(os.path.dirname(_HERE), "oracle", "_ref", "py")   # sourceless bytecode, see oracle/build_ref.py
 REF_ROOT = os.environ.get("SC_REFERENCE_ROOT", "/root/reference")
-if not os.path.isfile(os.path.join(REF_ROOT, "model", "renderer.py")) and os.path.isfile(os.path.join(STAGED_ROOT, "model", "renderer.pyc")):
-    REF_ROOT = STAGED_ROOT                     # the GPU box: the bytecode build_ref.stage_python() compiled from the reference
+STAGED = False
+if not os.path.isfile(os.path.join(REF_ROOT, "model", "renderer.py")) and os.path.isfile(os.path.join(STAGED_ROOT, "model", "renderer.refbc")):
+    REF_ROOT, STAGED = STAGED_ROOT, True       # the GPU box: the bytecode build_ref.stage_python() compiled from the reference
 
 
 def reference_available():
-    return (os.path.isfile(os.path.join(REF_ROOT, "model", "renderer.py"))
-            or os.path.isfile(os.path.join(REF_ROOT, "model", "renderer.pyc")))
+    return STAGED or os.path.isfile(os.path.join(REF_ROOT, "model", "renderer.py"))
 
 
 def source_available():
@@ -51,7 +51,11 @@ def import_reference():
         mpl.pyplot = _stub("matplotlib.pyplot")
     if "chamfer_3D" not in sys.modules:
         _stub("chamfer_3D")
-    if REF_ROOT not in sys.path:
+    if STAGED:
+        sys.path.insert(0, os.path.dirname(_HERE))
+        from oracle import build_ref
+        build_ref.install_staged_importer()
+    elif REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     import importlib
     mods = types.SimpleNamespace()

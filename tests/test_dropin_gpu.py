@@ -43,9 +43,10 @@ def test_reference_graph_train_step_under_shim(tmp_path):
     for k in ref["state"]:
         assert torch.equal(ref["state"][k], got["state"][k]), k
     assert torch.equal(ref["idx_NN"], got["idx_NN"])                   # same np.random.choice neighbour per sample
-    for k in ("proj_latent_sdf", "proj_latent_rgb", "pose", "scale_dist"):     # cuDNN vs CPU convolutions upstream of the renderer
-        assert _rel(got[k], ref[k]) < 5e-5, (k, _rel(got[k], ref[k]))
     report = {}
+    for k in ("proj_latent_sdf", "proj_latent_rgb", "pose", "scale_dist"):     # cuDNN vs CPU convolutions upstream of the renderer
+        report["cnn." + k] = _rel(got[k], ref[k])
+        assert report["cnn." + k] < 5e-5, (k, report["cnn." + k])
     for k in ("rgb_recon", "mask_recon", "depth_recon", "rgb_recon_NN_0", "mask_recon_NN_0"):
         err = float((got[k] - ref[k]).abs().max())
         report[k] = err
@@ -121,8 +122,9 @@ def test_reference_eval3d_functions_under_shim():
     e1, e2, j1, j2 = ours.chamfer_distance(opt, a, b)
     assert torch.equal(d1, e1) and torch.equal(d2, e2) and torch.equal(i1, j1) and torch.equal(i2, j2)
     o1, o2, k1, k2 = chamfer_ref.chamfer_forward(a.cpu().numpy(), b.cpu().numpy())
-    assert (d1.pow(2).cpu().numpy() - o1).max() < 1e-9 and (i1.cpu().numpy() == k1).all() and (i2.cpu().numpy() == k2).all()
+    assert (i1.cpu().numpy() == k1).all() and (i2.cpu().numpy() == k2).all()
     assert np.array_equal(np.sqrt(o1).astype(np.float32).view(np.int32), d1.cpu().numpy().view(np.int32))
+    assert np.array_equal(np.sqrt(o2).astype(np.float32).view(np.int32), d2.cpu().numpy().view(np.int32))
     f_ref = ref_eval.compute_fscore(d1, d2, opt.eval.f_thresholds)
     f_ours = ours.compute_fscore(d1, d2, opt.eval.f_thresholds)
     assert torch.equal(f_ref, f_ours) and f_ref.shape == (2, 6)
