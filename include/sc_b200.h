@@ -234,6 +234,40 @@ int sc_cosine_topk(const void* q_hi, const void* q_lo, const void* bank_hi, cons
                    int n_bank, int n_bank_valid, int dim, int k, float* sim_workspace, float* values,
                    int32_t* indices, cudaStream_t stream);
 
+/* ---- CLIP image tower, persistent single-kernel edition (csrc/clip_tower.cu) ---------------------------------
+ * Same contract as sc_clip_encode (clip_model.encode_image + F.normalize, CLIP_anno.py:166-167), executed as ONE cooperative
+ * launch: every GEMM a persistent warp-specialised tcgen05 pipeline with the accumulator double-buffered in TMEM, LayerNorm
+ * folded into the consuming GEMM, attention on mma.sync. cfg->split = 1: hi/lo bf16 operand pairs (fp32-class parity mode);
+ * cfg->split = 0: fp16 operands, one MMA per product (the precision the reference itself runs CLIP at on CUDA).
+ * The weights arrive PRE-FOLDED (shapeclipper_b200/clip.py::_pack_tower): W' = gain-scaled (and, for the q rows, 1/8-scaled)
+ * matrices as 16-bit planes (fp16 when split == 0, bf16 hi/lo when split == 1), s[n] = sum_k W'[n,k] of the ROUNDED planes,
+ * c[n] = sum_k ln_bias[k] W[n,k] + bias[n]. */
+typedef struct ScClipTowerLayer {
+    const void *qkv_w_hi, *qkv_w_lo; const float *qkv_s, *qkv_c;    /* [3W, W] folded with ln_1; s, c [3W] */
+    const void *out_w_hi, *out_w_lo; const float* out_b;            /* [W, W] */
+    const void *fc1_w_hi, *fc1_w_lo; const float *fc1_s, *fc1_c;    /* [4W, W] folded with ln_2 */
+    const void *fc2_w_hi, *fc2_w_lo; const float* fc2_b;            /* [W, 4W] */
+} ScClipTowerLayer;
+typedef struct ScClipTowerWeights {
+    const void *conv_w_hi, *conv_w_lo;                              /* [W, Kp] (columns zero-padded to a multiple of 64) */
+    const float *class_emb, *pos_emb, *lnpre_w, *lnpre_b, *lnpost_w, *lnpost_b;
+    const float* proj_t;                                            /* fp32 proj^T [out_dim, W] */
+    const ScClipTowerLayer* layers;                                 /* HOST array of cfg.layers entries */
+} ScClipTowerWeights;
+size_t sc_clip_tower_workspace_bytes(const ScClipConfig* cfg, int batch);
+size_t sc_clip_tower_plan_bytes(const ScClipConfig* cfg);
+/* Builds the phase table + every TMA descriptor once per (weights, batch, workspace) into `plan` (device memory). Synchronises
+ * `stream`; not capturable. */
+int sc_clip_tower_plan(const ScClipConfig* cfg, const ScClipTowerWeights* weights, int batch, void* workspace,
+                       size_t workspace_bytes, void* plan, size_t plan_bytes, int* n_phases_out, cudaStream_t stream);
+/* Diagnostics: byte offsets inside the workspace of {x fp32, x16 hi, lo, qkv hi, lo, attn hi, lo, h hi, lo, patch hi, lo,
+ * patch_out fp32, y fp32, raw fp32, stats a, stats b}. */
+int sc_clip_tower_workspace_layout(const ScClipConfig* cfg, int batch, size_t* offsets16);
+/* mode 0: one cooperative launch (+ one 4-byte memset); mode 1: one launch per phase (profiling form, same device code);
+ * mode k >= 2: per-phase launches of the first k - 1 phases only (diagnostics). */
+int sc_clip_tower_encode(const ScClipConfig* cfg, const void* plan, int n_phases, void* workspace, const float* images,
+                         float* emb, float* emb_unnormalised, void* emb_hi, void* emb_lo, int mode, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -197,6 +197,12 @@ def saved_buffer(device, batch, n_per_image, n_samples):
         return None                                    # the backward recomputes the forward per tile instead
 
 
+def saved_buffer_bytes(batch, n_per_image, n_samples):
+    """Bytes of saved activations one training render of this shape would keep for its backward (0 = the backward recomputes)."""
+    n = _lib.lib().sc_render_tc_saved_bytes(int(batch), int(n_per_image), int(n_samples))
+    return 0 if (n == 0 or n > SAVE_ACTIVATIONS_MAX_BYTES) else int(n)
+
+
 class KernelTimers:
     """Optional CUDA-event timing of the main kernels on their launch stream (bench.py's roofline numbers).
     Also counts every launch of a kernel of this library (bench.py's gpu_launches)."""

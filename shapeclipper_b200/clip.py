@@ -6,20 +6,32 @@
 
 Parameters carry openai/CLIP's `visual.*` names and shapes so real checkpoints load 1:1; without a checkpoint
 (no network in this environment) the tower is random-initialised with CLIP's init scales.
-GEMMs: tcgen05 tensor cores; `precision="split"` (default) feeds hi/lo bf16 operand pairs (3 MMAs per product,
-fp32-class accuracy), `precision="bf16"` is the plain-bf16 throughput mode.
+GEMMs: tcgen05 tensor cores. `precision="split"` (default) feeds hi/lo bf16 operand pairs (3 MMAs per product, fp32-class
+accuracy: the 1e-4 parity mode); `precision="fp16"` feeds fp16 operands, one MMA per product — the arithmetic `clip.load`
+itself uses on CUDA (CLIP_anno.py:16) — with an fp32 residual stream. Both run the whole tower as ONE persistent cooperative
+kernel (csrc/clip_tower.cu, host side clip_tower.py). `precision="bf16"` / `"split_v1"` select the round-1 kernel chain
+(csrc/clip_gemm.cu + clip_ops.cu: one launch per GEMM / LayerNorm / attention), kept as a cross-check.
 """
 import ctypes
 
 import torch
 
 from . import _lib
+from . import clip_tower as _tower
 
 CONFIGS = {
     "ViT-B/32": dict(image_size=224, patch=32, width=768, layers=12, heads=12, out_dim=512),
     "ViT-L/14": dict(image_size=224, patch=14, width=1024, layers=24, heads=16, out_dim=768),
     "tiny": dict(image_size=64, patch=32, width=128, layers=2, heads=2, out_dim=64),
 }
+PRECISIONS = ("split", "fp16", "split_v1", "bf16")
+PRECISION_NOTES = {
+    "split": "single persistent kernel; hi/lo bf16 operand pairs, 3 MMAs per product (fp32-class, 1e-4 parity mode): ceiling 1/3 of the bf16 peak",
+    "fp16": "single persistent kernel; fp16 operands, one MMA per product, fp32 accumulation and residual stream (the reference runs CLIP in fp16 on CUDA)",
+    "split_v1": "round-1 kernel chain (one launch per GEMM / LayerNorm / attention), hi/lo bf16 operand pairs",
+    "bf16": "round-1 kernel chain, plain bf16 operands, one MMA per product (about 1e-2 on the embedding)",
+}
+TOWER_PRECISIONS = ("split", "fp16")
 CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 _vp = ctypes.c_void_p
@@ -50,6 +62,7 @@ def declare(L):
     L.sc_clip_encode.restype = i
     L.sc_cosine_topk.argtypes = [_vp, _vp, _vp, _vp, i, i, i, i, i, _vp, _vp, _vp, _vp]
     L.sc_cosine_topk.restype = i
+    _tower.declare(L, ScClipConfig)
 
 
 def _p(t):
@@ -85,9 +98,13 @@ class CLIPVisual(torch.nn.Module):
 
     def __init__(self, name="ViT-B/32", precision="split", seed=0):
         super().__init__()
+        if precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % (PRECISIONS,))
         self.name = name
         self.cfg = dict(CONFIGS[name])
         self.precision = precision
+        self.per_phase_launches = False          # tower engine: one ordinary launch per phase instead of one cooperative launch
+        self._tower = None                       # (TowerWeights, cfg struct, {batch: TowerPlan})
         W, P, Ln = self.cfg["width"], self.cfg["patch"], self.cfg["layers"]
         T = (self.cfg["image_size"] // P) ** 2 + 1
         g = torch.Generator().manual_seed(seed)
@@ -125,7 +142,34 @@ class CLIPVisual(torch.nn.Module):
                 k = k[len("visual."):] if k.startswith("visual.") else k
                 if k in self._parameters:
                     self._parameters[k].copy_(v.to(self._parameters[k].dtype))
+        self._invalidate()
+
+    def _invalidate(self):
         self._packed = None
+        self._tower = None
+
+    def _apply(self, fn, *a, **k):               # .to() / .cuda() / .float(): packed device copies point at the old tensors
+        self._invalidate()
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._invalidate()
+        return super().load_state_dict(*a, **k)
+
+    def _tower_state(self, batch):
+        P_ = self._parameters
+        dev = P_["proj"].device
+        _lib.require_cuda(P_["proj"])
+        if self._tower is None:
+            split = self.precision == "split"
+            cfg = ScClipConfig(split=1 if split else 0, **self.cfg)
+            self._tower = (_tower.TowerWeights(P_, self.cfg, split), cfg, {})
+        w, cfg, plans = self._tower
+        if batch not in plans:
+            if len(plans) >= 4:
+                plans.clear()
+            plans[batch] = _tower.TowerPlan(cfg, w, batch, dev)
+        return cfg, plans[batch], dev
 
     def _pack(self):
         if self._packed is not None:
@@ -134,7 +178,7 @@ class CLIPVisual(torch.nn.Module):
         dev = P_["proj"].device
         _lib.require_cuda(P_["proj"])
         keep = []
-        split = self.precision == "split"
+        split = self.precision == "split_v1"
 
         def mat(t):
             hi, lo = split_bf16(t.detach().float().contiguous())
@@ -173,12 +217,22 @@ class CLIPVisual(torch.nn.Module):
     @torch.no_grad()
     def encode(self, images, want_planes=False):
         """images [B,3,S,S] fp32 CUDA, CLIP-normalised -> (unnormalised emb, L2-normalised emb[, hi, lo planes])."""
-        cfg, w, _layers, _keep, dev = self._pack()
         L = _lib.lib()
         _lib.require_cuda(images)
         img = images.float().contiguous()
         B = img.shape[0]
         D = self.cfg["out_dim"]
+        from . import _render_native as rn
+        if self.precision in TOWER_PRECISIONS:
+            cfg, plan, dev = self._tower_state(B)
+            raw = torch.empty(B, D, device=dev); emb = torch.empty(B, D, device=dev)
+            hi = torch.empty(B, D, device=dev, dtype=torch.bfloat16) if want_planes else None
+            lo = torch.empty(B, D, device=dev, dtype=torch.bfloat16) if want_planes else None
+            with rn.TIMERS.span("clip_encode", dev):
+                n = _tower.encode(cfg, plan, img, emb, raw, hi, lo, per_phase_launches=self.per_phase_launches)
+            rn.TIMERS.count(n)
+            return (raw, emb, hi, lo) if want_planes else (raw, emb)
+        cfg, w, _layers, _keep, dev = self._pack()
         raw = torch.empty(B, D, device=dev); emb = torch.empty(B, D, device=dev)
         hi = torch.empty(B, D, device=dev, dtype=torch.bfloat16) if want_planes else None
         lo = torch.empty(B, D, device=dev, dtype=torch.bfloat16) if want_planes else None
@@ -290,8 +344,9 @@ def calc_matches(features, k_nearest=6, bank=None, thres=None):
 class _BenchContext:
     """CLIP leg of bench.py: encode the batch images (ViT-B/32, random init) and look up the 6 nearest of a 4096 bank."""
 
-    def __init__(self, opt, batch, device, bank_size=4096):
-        self.model = CLIPVisual("ViT-B/32", precision="split").to(device)
+    def __init__(self, opt, batch, device, bank_size=4096, precision="split"):
+        self.model = CLIPVisual("ViT-B/32", precision=precision).to(device)
+        self.launches = (2 if precision in TOWER_PRECISIONS else 5 + 7 * self.model.cfg["layers"] + 3) + 2
         self.device = device
         g = torch.Generator().manual_seed(7)
         self.host_images = [torch.randn(batch, 3, 224, 224, generator=g).pin_memory() for _ in range(2)]
@@ -320,5 +375,5 @@ class _BenchContext:
         return self.idx
 
 
-def bench_context(opt, batch, device):
-    return _BenchContext(opt, batch, device)
+def bench_context(opt, batch, device, precision="split"):
+    return _BenchContext(opt, batch, device, precision=precision)

@@ -52,9 +52,14 @@ class FlatGradients:
         self.flat.zero_()
 
     def all_reduce(self):
+        """Mean over ranks, in place: ONE collective. NCCL's AVG folds the 1/world scale into the reduction (no separate
+        scaling kernel over the 147 MB buffer); gloo (CPU tests) has no AVG, so it sums and scales."""
         if self.world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.mul_(1.0 / self.world)
+            if dist.get_backend() == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+                self.flat.mul_(1.0 / self.world)
 
     def broadcast_parameters(self, src=0):
         if self.world > 1:

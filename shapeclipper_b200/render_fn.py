@@ -16,6 +16,9 @@ import os as _os
 PRECISION = {"forward": _os.environ.get("SC_RENDER_FORWARD", "tc"), "backward": _os.environ.get("SC_RENDER_BACKWARD", "tc")}
 
 
+STEP_PRECISIONS = ("tc",)          # render arithmetic modes bench.py's configs[2] record steps through
+
+
 SAVE_ACTIVATIONS = _os.environ.get("SC_RENDER_SAVE_ACTIVATIONS", "1") != "0"
 
 

@@ -5,13 +5,17 @@
 
 The reference runs this as ~2 000 eager kernel launches with ~20 host syncs. Here the step is launch-bound once the
 renders are fused (two render kernels each way + ~350 small torch kernels for rays, losses and Adam), so `TrainStep`
-captures it ONCE into CUDA graphs (forward + losses + backward in one, the optimiser in another; the NCCL all-reduce
-between them stays eager) and replays them: same kernels, same arithmetic, no per-launch host cost.
+captures it ONCE into a CUDA graph — forward + losses + backward, the NCCL gradient all-reduce (averaging, N > 1) and the
+optimiser step in ONE graph, so a step is a single replay with no host gap around the collective — and replays it: same
+kernels, same arithmetic, no per-launch host cost. (`SC_ALLREDUCE_IN_GRAPH=0` keeps the collective eager between two
+graphs, the round-1 structure.)
 
 Requirements for capture (checked): `opt.render.device_rng` and `opt.reg.device_sampling` (every random draw on the
 CUDA generator, no host round trip) and a capturable optimiser (`torch.optim.Adam(..., capturable=True)`).
 Without them the step runs eagerly with identical results to calling the pieces by hand.
 """
+import os
+
 import torch
 
 from . import _render_native as rn
@@ -97,12 +101,19 @@ class TrainStep:
         rn.TIMERS.enabled = timers_were
         rn.TIMERS.capturing = True
         n0 = rn.TIMERS.launches
+        self._single = self.flat.world == 1 or os.environ.get("SC_ALLREDUCE_IN_GRAPH", "1") != "0"
+        # NCCL's watchdog thread polls CUDA events while we capture: relaxed mode keeps its calls from invalidating the capture
+        kw = dict(capture_error_mode="thread_local") if self.flat.world > 1 else {}
         self._g_main = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._g_main):
+        with torch.cuda.graph(self._g_main, **kw):
             self.loss = self._forward_backward()
-        self._g_optim = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._g_optim, pool=self._g_main.pool()):
-            self.optim.step()
+            if self._single:
+                self.flat.all_reduce()
+                self.optim.step()
+        if not self._single:
+            self._g_optim = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._g_optim, pool=self._g_main.pool()):
+                self.optim.step()
         rn.TIMERS.capturing = False
         self.launches_per_step = rn.TIMERS.launches - n0
         rn.TIMERS.launches = n0
@@ -117,8 +128,9 @@ class TrainStep:
             self.optim.step()
             return self.loss
         self._g_main.replay()
-        self.flat.all_reduce()
-        self._g_optim.replay()
+        if not self._single:
+            self.flat.all_reduce()
+            self._g_optim.replay()
         # a replayed optimiser step rewrites the weights without bumping their version counters: packed weight blobs cached
         # by eager callers (validation renders, eval_3D.compute_level_grid) would otherwise stay at the first call's weights
         rn.invalidate_blob_cache()
