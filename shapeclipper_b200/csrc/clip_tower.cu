@@ -18,7 +18,7 @@
 // stream, together with per-row (mean, M2) partials of its BN columns; the consumer's epilogue merges the partials (Chan) into
 // mean / rstd. No LayerNorm kernel, no normalised activation tensor.
 // Attention runs on mma.sync m16n8k16 from ldmatrix-fed shared-memory tiles (64 queries x 64 keys per 4-warp group, online
-// softmax over key tiles), two (image, head, query-tile) items per CTA at a time.
+// softmax over key tiles), three (image, head, query-tile) items per CTA at a time.
 //
 // Two arithmetic modes (template SPLIT): 1 = fp16 operands, one MMA per product — the reference's own precision (clip.load
 // returns an fp16 model on CUDA, CLIP_anno.py:16) with an fp32 residual stream and fp32 accumulation; 3 = hi/lo bf16 operand
@@ -28,6 +28,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -38,7 +39,7 @@
 namespace sctw {
 using namespace sctc;
 
-enum { PH_GEMM = 0, PH_ATTN = 1, PH_IM2COL = 2, PH_TOKENS = 3, PH_LNPOST = 4, PH_PROJ = 5, PH_L2NORM = 6 };
+enum { PH_GEMM = 0, PH_ATTN = 1, PH_IM2COL = 2, PH_TOKENS = 3, PH_HEAD = 4, PH_L2NORM = 5 };
 enum { EPI_F32 = 0, EPI_LN16 = 1, EPI_RESID = 2 };
 
 struct alignas(16) Phase {
@@ -49,16 +50,16 @@ struct alignas(16) Phase {
     int S, Kp, D, pad0;                   // image size, padded im2col K, out dim
     const float* v0;                      // EPI_LN16: s[N]      | TOKENS: class_emb | LNPOST: gain  | PROJ: proj^T [D, W]
     const float* v1;                      // EPI_LN16: c[N]; else bias[N] or null | TOKENS: pos_emb | LNPOST: bias
-    const float* v2;                      // TOKENS: ln_pre gain
+    const float* v2;                      // TOKENS: ln_pre gain | HEAD: proj^T [D, W]
     const float* v3;                      // TOKENS: ln_pre bias
     float* f0;                            // GEMM: fp32 out / residual stream x | TOKENS: x | LNPOST: y [B, W] | PROJ: raw emb | L2NORM: raw emb
-    const float* f1;                      // TOKENS: patch_out | LNPOST: x | PROJ: y | IM2COL: images (null = kernel argument)
+    const float* f1;                      // TOKENS: patch_out | HEAD: x | IM2COL: images (null = kernel argument)
     void* o_hi; void* o_lo;               // 16-bit output planes
     const void* i_hi; const void* i_lo;   // ATTN: qkv planes
     const float2* st_in; float2* st_out;  // LN partial statistics [M, parts]
 };
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;             // warp 0 TMA, 1 MMA issue, 2 TMEM owner, 3 spare, 4..11 epilogue; 3 x 4-warp attention groups
 constexpr int kTileBytes = 196 * 1024;    // operand ring / attention staging
 constexpr int kMaxStages = 8;
 constexpr int kSmemBytes = kTileBytes + 1024 + 512;
@@ -118,7 +119,7 @@ __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target) {
         target += gridDim.x;
         __threadfence();
         atomicAdd(counter, 1u);
-        while (ld_acquire_u32(counter) < target) { __nanosleep(32); }
+        while (ld_acquire_u32(counter) < target) { }
         __threadfence();
     }
     __syncthreads();
@@ -132,26 +133,129 @@ struct Smem {
 };
 
 // ------------------------------------------------------------------------------------------------ GEMM phase
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one FULL 32-byte sector per thread and instruction. The epilogue's accesses
+// are row-strided (thread = accumulator row), so every lane touches its own sector; with 128-bit accesses each sector was requested
+// twice and the L2 request rate, not bytes, bounded the residual epilogues (measured: 17 of 37 us in out-proj).
+// QuickGELU x sigmoid(1.702 x). Parity mode: exp + reciprocal (two SFU ops per element). fp16 mode: sigmoid(z) = 0.5 tanh(z / 2) + 0.5
+// with tanh.approx (ONE SFU op, max relative error 2^-11 = the fp16 rounding of the result): the 128 x 192 fc1 tiles were SFU-paced.
 template <int SPLIT>
-__device__ __forceinline__ void gemm_phase(const Phase& ph, const CUtensorMap* maps, const Smem& sm, uint32_t tmem_base,
+__device__ __forceinline__ float quick_gelu(float x) {
+    if (SPLIT == 3) return __fdividef(x, 1.f + __expf(-1.702f * x));
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
+}
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ldcg256(const float* p) {
+    F8 r;
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void st256u(void* p, const uint32_t* h) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]), "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7]) : "memory");
+}
+
+// Epilogue of one 16-column chunk of this thread's row. Every per-phase parameter arrives in registers (the Phase lives in shared
+// memory and the tcgen05 asm blocks clobber memory: reading it inside the loop costs a dependent LDS + LDG chain per element).
+// `rs` = this chunk's residual values (EPI_RESID), loaded by the caller one chunk ahead.
+template <int SPLIT, int EPI>
+__device__ __forceinline__ void epi_chunk(uint32_t taddr, bool row_ok, size_t off, int col0, int act, int dbg, float mean, float rstd,
+                                          const float* __restrict__ v0, const float* __restrict__ v1, float* __restrict__ f0,
+                                          typename E16<SPLIT>::t* __restrict__ o_hi, typename E16<SPLIT>::t* __restrict__ o_lo,
+                                          const F8& rs0, const F8& rs1, float& r_n, float& r_mean, float& r_m2)
+{
+    typedef E16<SPLIT> E;
+    float4 p0[4], p1[4];
+    if (EPI == EPI_LN16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { p0[i] = __ldg(reinterpret_cast<const float4*>(v0 + col0) + i); p1[i] = __ldg(reinterpret_cast<const float4*>(v1 + col0) + i); }
+    } else if (v1 != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p1[i] = __ldg(reinterpret_cast<const float4*>(v1 + col0) + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float v[16];
+    tmem_ld_16(taddr, v);
+    if (EPI == EPI_LN16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[4 * i + 0] = rstd * (v[4 * i + 0] - mean * p0[i].x) + p1[i].x;
+            v[4 * i + 1] = rstd * (v[4 * i + 1] - mean * p0[i].y) + p1[i].y;
+            v[4 * i + 2] = rstd * (v[4 * i + 2] - mean * p0[i].z) + p1[i].z;
+            v[4 * i + 3] = rstd * (v[4 * i + 3] - mean * p0[i].w) + p1[i].w;
+        }
+        if (act == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = quick_gelu<SPLIT>(v[i]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[4 * i] += p1[i].x; v[4 * i + 1] += p1[i].y; v[4 * i + 2] += p1[i].z; v[4 * i + 3] += p1[i].w; }
+        if (EPI == EPI_RESID) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { v[i] += rs0.v[i]; v[8 + i] += rs1.v[i]; }
+        }
+    }
+    if (!row_ok) return;
+    if (EPI != EPI_LN16 && !(dbg & 2)) { st256(f0 + off, v); st256(f0 + off + 8, v + 8); }
+    if (EPI != EPI_F32 && !(dbg & 4)) {
+        uint32_t h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) h[i] = E::pack(v[2 * i], v[2 * i + 1]);
+        st256u(o_hi + off, h);
+        if (SPLIT == 3) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h[i] = E::pack(E::lo_of(v[2 * i]), E::lo_of(v[2 * i + 1]));
+            st256u(o_lo + off, h);
+        }
+    }
+    if (EPI == EPI_RESID) {                                          // (mean, M2) of these 16 columns, merged into the running pair (Chan)
+        float mc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mc += v[i];
+        mc *= (1.f / 16.f);
+        float qc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float d = v[i] - mc; qc += d * d; }
+        const float nn = r_n + 16.f, d = mc - r_mean;
+        r_m2 += qc + d * d * r_n * 16.f / nn;
+        r_mean += d * 16.f / nn;
+        r_n = nn;
+    }
+}
+
+template <int SPLIT>
+__device__ __forceinline__ void gemm_phase(const Phase& ph_smem, const CUtensorMap* maps, const Smem& sm, uint32_t tmem_base,
                                            uint32_t& ring_par, uint32_t& acc_it)
 {
     typedef E16<SPLIT> E;
     constexpr int PL = (SPLIT == 3) ? 2 : 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int BN = ph.BN;
+    // per-phase parameters into registers, once
+    const int BN = ph_smem.BN, M = ph_smem.M, N = ph_smem.N, K = ph_smem.K, epi = ph_smem.epi, act = ph_smem.act;
     const int a_bytes = 128 * 64 * 2, w_bytes = BN * 64 * 2;
     const int stage_bytes = PL * (a_bytes + w_bytes);
     int ns = kTileBytes / stage_bytes;
     ns = ns > kMaxStages ? kMaxStages : ns;
-    const int MT = (ph.M + 127) / 128, NT = ph.N / BN, num_kb = ph.K / 64;
+    const int MT = (M + 127) / 128, NT = N / BN, num_kb = K / 64;
     const int tiles = MT * NT;
 
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
         if (lane == 0) {
-            const CUtensorMap* mAh = maps + ph.map_a;
-            const CUtensorMap* mWh = maps + ph.map_w;
+            const CUtensorMap* mAh = maps + ph_smem.map_a;
+            const CUtensorMap* mWh = maps + ph_smem.map_w;
+            tma_prefetch_desc(mAh); tma_prefetch_desc(mWh);
+            if (SPLIT == 3) { tma_prefetch_desc(mAh + 1); tma_prefetch_desc(mWh + 1); }
             int s = 0;
             for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
                 const int m0 = (t % MT) * 128, n0 = (t / MT) * BN;
@@ -206,97 +310,65 @@ __device__ __forceinline__ void gemm_phase(const Phase& ph, const CUtensorMap* m
             }
         }
     } else if (warp >= 4) {
-        // ---------------------------------------------------------------- epilogue: TMEM lane quarter = warp & 3
-        const int q = warp & 3;
-        typename E::t* o_hi = reinterpret_cast<typename E::t*>(ph.o_hi);
-        typename E::t* o_lo = reinterpret_cast<typename E::t*>(ph.o_lo);
+        // ---------------------------------------------------------------- epilogue: 8 warps; TMEM lane quarter = warp & 3, column half = (warp - 4) >> 2
+        const int q = warp & 3, half = (warp - 4) >> 2;
+        const int hw = BN >> 1, cb = half * hw;
+        typename E::t* o_hi = reinterpret_cast<typename E::t*>(ph_smem.o_hi);
+        typename E::t* o_lo = reinterpret_cast<typename E::t*>(ph_smem.o_lo);
+        const float* v0 = ph_smem.v0; const float* v1 = ph_smem.v1; float* f0 = ph_smem.f0;
+        const float2* st_in = ph_smem.st_in; float2* st_out = ph_smem.st_out;
+        const int parts_in = ph_smem.parts_in, cnt_in = ph_smem.cnt_in, dbg = ph_smem.pad0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
             const int mt = t % MT, nt = t / MT;
             const int m0 = mt * 128, n0 = nt * BN;
             const uint32_t buf = acc_it & 1u;
             const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < ph.M;
-            // LayerNorm statistics of this row (merge of the partials the producer of x left behind)
+            const bool row_ok = row < M;
+            // LayerNorm statistics of this row (Chan merge of the partials the producer of x left behind)
             float mean = 0.f, rstd = 1.f;
-            if (ph.epi == EPI_LN16 && row_ok) {
-                const float2* sp = ph.st_in + (size_t)row * ph.parts_in;
-                float mu = 0.f;
-                for (int j = 0; j < ph.parts_in; ++j) mu += __ldcg(&sp[j]).x;
-                mu /= (float)ph.parts_in;
-                float m2 = 0.f;
-                for (int j = 0; j < ph.parts_in; ++j) { const float2 pj = __ldcg(&sp[j]); const float d = pj.x - mu; m2 += pj.y + (float)ph.cnt_in * d * d; }
+            if (epi == EPI_LN16 && row_ok) {
+                const float2* sp = st_in + (size_t)row * parts_in;
+                float mu = 0.f, m2 = 0.f;
+                for (int j = 0; j < parts_in; ++j) mu += __ldcg(&sp[j]).x;
+                mu /= (float)parts_in;
+                for (int j = 0; j < parts_in; ++j) { const float2 pj = __ldcg(&sp[j]); const float d = pj.x - mu; m2 += pj.y + (float)cnt_in * d * d; }
                 mean = mu;
-                rstd = rsqrtf(m2 / (float)(ph.parts_in * ph.cnt_in) + 1e-5f);
+                rstd = rsqrtf(m2 / (float)(parts_in * cnt_in) + 1e-5f);
             }
             mbar_wait(sm.tfull + buf, (acc_it >> 1) & 1u);
             tc_fence_after();
             const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u;
             float r_n = 0.f, r_mean = 0.f, r_m2 = 0.f;                       // running statistics of the new x row (EPI_RESID)
+            const size_t row_off = (size_t)row * N + n0;
+            F8 z8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z8.v[i] = 0.f;
+            if (epi == EPI_LN16) {
+#pragma unroll 2
+                for (int c = cb; c < cb + hw; c += 16)
+                    epi_chunk<SPLIT, EPI_LN16>(trow + (uint32_t)c, row_ok, row_off + c, n0 + c, act, dbg, mean, rstd, v0, v1, f0, o_hi, o_lo, z8, z8, r_n, r_mean, r_m2);
+            } else if (epi == EPI_RESID) {
+                // the residual does not depend on the MMA: its loads run one chunk ahead of the accumulator reads
+                const bool ld_ok = row_ok && !(dbg & 1);
+                F8 a0 = z8, a1 = z8;
+                if (ld_ok) { a0 = ldcg256(f0 + row_off + cb); a1 = ldcg256(f0 + row_off + cb + 8); }
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                float v[16];
-                tmem_ld_16(trow + (uint32_t)c, v);
-                const int col0 = n0 + c;
-                const size_t off = (size_t)row * ph.N + col0;
-                if (ph.epi == EPI_LN16) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float x = rstd * (v[i] - mean * __ldg(ph.v0 + col0 + i)) + __ldg(ph.v1 + col0 + i);
-                        if (ph.act == 1) x = x / (1.f + __expf(-1.702f * x));
-                        v[i] = x;
-                    }
-                } else {
-                    if (ph.v1 != nullptr) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) v[i] += __ldg(ph.v1 + col0 + i);
-                    }
-                    if (ph.epi == EPI_RESID && row_ok) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 r = __ldcg(reinterpret_cast<const float4*>(ph.f0 + off + i));
-                            v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
-                        }
-                    }
+                for (int c = cb; c < cb + hw; c += 16) {
+                    F8 b0 = z8, b1 = z8;
+                    if (ld_ok && c + 16 < cb + hw) { b0 = ldcg256(f0 + row_off + c + 16); b1 = ldcg256(f0 + row_off + c + 24); }
+                    epi_chunk<SPLIT, EPI_RESID>(trow + (uint32_t)c, row_ok, row_off + c, n0 + c, act, dbg, mean, rstd, v0, v1, f0, o_hi, o_lo, a0, a1, r_n, r_mean, r_m2);
+                    a0 = b0; a1 = b1;
                 }
-                if (row_ok) {
-                    if (ph.epi != EPI_LN16) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(ph.f0 + off + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    }
-                    if (ph.epi != EPI_F32) {
-                        uint32_t h[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) h[i] = E::pack(v[2 * i], v[2 * i + 1]);
-                        *reinterpret_cast<uint4*>(o_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                        *reinterpret_cast<uint4*>(o_hi + off + 8) = make_uint4(h[4], h[5], h[6], h[7]);
-                        if (SPLIT == 3) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) h[i] = E::pack(E::lo_of(v[2 * i]), E::lo_of(v[2 * i + 1]));
-                            *reinterpret_cast<uint4*>(o_lo + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                            *reinterpret_cast<uint4*>(o_lo + off + 8) = make_uint4(h[4], h[5], h[6], h[7]);
-                        }
-                    }
-                    if (ph.epi == EPI_RESID) {                              // (mean, M2) of these 16 columns, merged into the running pair
-                        float mc = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) mc += v[i];
-                        mc *= (1.f / 16.f);
-                        float qc = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) { const float d = v[i] - mc; qc += d * d; }
-                        const float nn = r_n + 16.f, d = mc - r_mean;
-                        r_m2 += qc + d * d * r_n * 16.f / nn;
-                        r_mean += d * 16.f / nn;
-                        r_n = nn;
-                    }
-                }
+            } else {
+#pragma unroll 2
+                for (int c = cb; c < cb + hw; c += 16)
+                    epi_chunk<SPLIT, EPI_F32>(trow + (uint32_t)c, row_ok, row_off + c, n0 + c, act, dbg, mean, rstd, v0, v1, f0, o_hi, o_lo, z8, z8, r_n, r_mean, r_m2);
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(sm.tempty + buf);                     // accumulator buffer free for tile i+2
-            if (ph.epi == EPI_RESID && row_ok && ph.st_out != nullptr)
-                ph.st_out[(size_t)row * NT + nt] = make_float2(r_mean, r_m2);
+            if (lane == 0) mbar_arrive(sm.tempty + buf);                     // accumulator buffer free for tile i+2 (8 arrivals)
+            if (epi == EPI_RESID && row_ok && st_out != nullptr)
+                st_out[(size_t)row * (2 * NT) + 2 * nt + half] = make_float2(r_mean, r_m2);
             ++acc_it;
         }
     }
@@ -341,7 +413,7 @@ __device__ __forceinline__ void attention_phase(const Phase& ph, uint8_t* tiles)
     const int g = lane >> 2, tq = lane & 3;
     const float kLog2e = 1.4426950408889634f;
 
-    for (int it = 2 * blockIdx.x + grp; it < items; it += 2 * gridDim.x) {
+    for (int it = 3 * blockIdx.x + grp; it < items; it += 3 * gridDim.x) {
         const int qt = it % QT, h = (it / QT) % H, b = it / (QT * H);
         const size_t row_base = (size_t)b * T;
         const int q0 = qt * 64;
@@ -473,113 +545,162 @@ __device__ __forceinline__ void attention_phase(const Phase& ph, uint8_t* tiles)
 }
 
 // ------------------------------------------------------------------------------------------------ element-wise phases
-// images [B,3,S,S] fp32 -> patches [B*G*G, Kp] 16-bit planes; column = c*P*P + py*P + px (conv1.weight flattening), zero padding to Kp
+// images [B,3,S,S] fp32 -> patches [B*G*G, Kp] 16-bit planes; column = c*P*P + py*P + px (conv1.weight flattening). The padding
+// columns [3*P*P, Kp) are never written: the workspace is zero-filled when the plan is made.
+// Unit of work = one pixel row of one patch channel (P contiguous floats in, P contiguous 16-bit values out), handled by 8 lanes
+// with vector loads; four units per group in flight (one CTA per SM: instruction-level parallelism is the only latency hiding),
+// 32-bit index arithmetic only (the first version spent its time in 64-bit divisions).
+template <int SPLIT, int VEC>
+__device__ __forceinline__ void im2col_rows(const Phase& ph, const float* images)
+{
+    typedef E16<SPLIT> E;
+    typename E::t* hi = reinterpret_cast<typename E::t*>(ph.o_hi);
+    typename E::t* lo = reinterpret_cast<typename E::t*>(ph.o_lo);
+    const int S = ph.S, P = ph.P, G = S / P, Kp = ph.Kp, PP = P * P;
+    const int units = ph.B * G * G * 3 * P;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, l8 = gtid & 7;
+    const int ngroups = (gridDim.x * blockDim.x) >> 3;
+    const int px = l8 * VEC;
+    constexpr int U = 4;
+    for (int u0 = gtid >> 3; u0 < units; u0 += ngroups * U) {
+        float v[U][VEC];
+        int dst[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int u = u0 + k * ngroups;
+            dst[k] = -1;
+            if (u < units && px < P) {
+                const int py = u % P, t = u / P, c = t % 3, row = t / 3;
+                const int gx = row % G, t2 = row / G, gy = t2 % G, bb = t2 / G;
+                const float* src = images + (((size_t)bb * 3 + c) * S + gy * P + py) * S + gx * P + px;
+                if (VEC == 4) { const float4 q = __ldg(reinterpret_cast<const float4*>(src)); v[k][0] = q.x; v[k][1] = q.y; v[k][VEC - 2] = q.z; v[k][VEC - 1] = q.w; }
+                else { const float2 q = __ldg(reinterpret_cast<const float2*>(src)); v[k][0] = q.x; v[k][1] = q.y; }
+                dst[k] = row * Kp + c * PP + py * P + px;            // < 2^31 for every supported shape (checked by the host)
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (dst[k] < 0) continue;
+            if (VEC == 4) {
+                *reinterpret_cast<uint2*>(hi + dst[k]) = make_uint2(E::pack(v[k][0], v[k][1]), E::pack(v[k][VEC - 2], v[k][VEC - 1]));
+                if (SPLIT == 3) *reinterpret_cast<uint2*>(lo + dst[k]) = make_uint2(E::pack(E::lo_of(v[k][0]), E::lo_of(v[k][1])), E::pack(E::lo_of(v[k][VEC - 2]), E::lo_of(v[k][VEC - 1])));
+            } else {
+                *reinterpret_cast<uint32_t*>(hi + dst[k]) = E::pack(v[k][0], v[k][1]);
+                if (SPLIT == 3) *reinterpret_cast<uint32_t*>(lo + dst[k]) = E::pack(E::lo_of(v[k][0]), E::lo_of(v[k][1]));
+            }
+        }
+    }
+}
 template <int SPLIT>
 __device__ __forceinline__ void im2col_phase(const Phase& ph, const float* images)
 {
-    typedef E16<SPLIT> E;
-    typename E::t* hi = reinterpret_cast<typename E::t*>(ph.o_hi);
-    typename E::t* lo = reinterpret_cast<typename E::t*>(ph.o_lo);
-    const int S = ph.S, P = ph.P, G = S / P, Kc = 3 * P * P, Kp = ph.Kp;
-    const size_t total2 = (size_t)ph.B * G * G * Kp / 2;                      // pairs of columns (P and Kp are even)
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total2; i += (size_t)gridDim.x * blockDim.x) {
-        const int col = (int)((2 * i) % Kp);
-        const size_t row = (2 * i) / Kp;
-        float a = 0.f, b = 0.f;
-        if (col < Kc) {
-            const int px = col % P, py = (col / P) % P, c = col / (P * P);
-            const int gx = (int)(row % G), gy = (int)((row / G) % G), bb = (int)(row / ((size_t)G * G));
-            const float2 v = __ldg(reinterpret_cast<const float2*>(images + (((size_t)bb * 3 + c) * S + gy * P + py) * S + gx * P + px));
-            a = v.x; b = v.y;
-        }
-        reinterpret_cast<uint32_t*>(hi)[i] = E::pack(a, b);
-        if (SPLIT == 3) reinterpret_cast<uint32_t*>(lo)[i] = E::pack(E::lo_of(a), E::lo_of(b));
-    }
+    if (ph.P == 32) im2col_rows<SPLIT, 4>(ph, images);      // 8 lanes x 4 pixels
+    else im2col_rows<SPLIT, 2>(ph, images);                 // P <= 16, even (ViT-L/14: 7 of 8 lanes active)
 }
 
-// one warp per token row: x = LN_pre((class | patch) + pos) -> fp32 stream, 16-bit planes, (mean, M2) partials per `cnt` columns
-template <int SPLIT>
-__device__ __forceinline__ void tokens_phase(const Phase& ph)
+// one warp per token row: x = LN_pre((class | patch) + pos) -> fp32 stream, 16-bit planes, (mean, M2) of the row
+template <int SPLIT, int PER>
+__device__ __forceinline__ void tokens_rows(const Phase& ph)
 {
     typedef E16<SPLIT> E;
     typename E::t* hi = reinterpret_cast<typename E::t*>(ph.o_hi);
     typename E::t* lo = reinterpret_cast<typename E::t*>(ph.o_lo);
-    const int W = ph.W, T = ph.T, lane = threadIdx.x & 31;
+    const int W = ph.W, T = ph.T, M = ph.M, lane = threadIdx.x & 31;
+    const float* cls = ph.v0; const float* pos = ph.v1; const float* gain = ph.v2; const float* bias = ph.v3; const float* patch = ph.f1;
+    float* x = ph.f0; float2* st = ph.st_out;
     const int wpb = blockDim.x >> 5;
-    const int per = W / 32;                                                   // <= 32 (W <= 1024)
-    const int parts = W / ph.BN;                                              // BN = columns per statistics partial
-    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < ph.M; row += gridDim.x * wpb) {
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
         const int b = row / T, tk = row % T;
-        float v[32];
+        float v[PER];
         float s = 0.f;
-        for (int i = 0; i < per; ++i) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
             const int c = i * 32 + lane;
-            const float t = (tk == 0 ? __ldg(ph.v0 + c) : __ldcg(ph.f1 + ((size_t)b * (T - 1) + tk - 1) * W + c)) + __ldg(ph.v1 + (size_t)tk * W + c);
-            v[i] = t; s += t;
+            v[i] = (tk == 0 ? __ldg(cls + c) : __ldcg(patch + ((size_t)b * (T - 1) + tk - 1) * W + c)) + __ldg(pos + (size_t)tk * W + c);
+            s += v[i];
         }
         const float mean = warp_sum(s) / W;
         float qv = 0.f;
-        for (int i = 0; i < per; ++i) { const float d = v[i] - mean; qv += d * d; }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { const float d = v[i] - mean; qv += d * d; }
         const float rstd = rsqrtf(warp_sum(qv) / W + 1e-5f);
-        for (int i = 0; i < per; ++i) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
             const int c = i * 32 + lane;
-            v[i] = (v[i] - mean) * rstd * __ldg(ph.v2 + c) + __ldg(ph.v3 + c);
+            v[i] = (v[i] - mean) * rstd * __ldg(gain + c) + __ldg(bias + c);
             const size_t o = (size_t)row * W + c;
-            ph.f0[o] = v[i];
+            x[o] = v[i];
             hi[o] = E::one(v[i]);
             if (SPLIT == 3) lo[o] = E::one(E::lo_of(v[i]));
         }
-        // partial statistics of the NORMALISED row, per BN-column segment (column c belongs to segment c / BN)
-        for (int p = 0; p < parts; ++p) {
-            float ss = 0.f;
-            for (int i = 0; i < per; ++i) { const int c = i * 32 + lane; if (c / ph.BN == p) ss += v[i]; }
-            const float mp = warp_sum(ss) / ph.BN;
-            float qq = 0.f;
-            for (int i = 0; i < per; ++i) { const int c = i * 32 + lane; if (c / ph.BN == p) { const float d = v[i] - mp; qq += d * d; } }
-            qq = warp_sum(qq);
-            if (lane == 0) ph.st_out[(size_t)row * parts + p] = make_float2(mp, qq);
+        // statistics of the NORMALISED row as ONE (mean, M2) part over all W columns (the first QKV GEMM merges parts_in = 1)
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) ss += v[i];
+        const float mp = warp_sum(ss) / W;
+        float qq = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { const float d = v[i] - mp; qq += d * d; }
+        qq = warp_sum(qq);
+        if (lane == 0) st[row] = make_float2(mp, qq);
+    }
+}
+template <int SPLIT>
+__device__ __forceinline__ void tokens_phase(const Phase& ph)
+{
+    switch (ph.W / 32) {
+        case 24: tokens_rows<SPLIT, 24>(ph); break;      // ViT-B
+        case 32: tokens_rows<SPLIT, 32>(ph); break;      // ViT-L
+        case 16: tokens_rows<SPLIT, 16>(ph); break;
+        case 8:  tokens_rows<SPLIT, 8>(ph); break;
+        default: tokens_rows<SPLIT, 4>(ph); break;       // W = 128 (test configuration); the host rejects other widths
+    }
+}
+
+// head, part 1: raw[b, d0 .. d0+127] = LN_post(x[b, class token]) @ proj for one (image, 128-output block) per CTA and pass:
+// LayerNorm by warp 0 into shared memory (recomputed per block: 768 values), the dot products spread over the CTA's warps two
+// at a time (fp32 FMA, proj^T rows from L2).
+constexpr int kHeadBlock = 128;
+__device__ __forceinline__ void head_phase(const Phase& ph, float* smem_f)
+{
+    const int W = ph.W, D = ph.D, T = ph.T, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const float* gain = ph.v0; const float* bias = ph.v1; const float* projT = ph.v2; const float* xs = ph.f1;
+    float* raw = ph.f0;
+    float* y = smem_f;                 // [W]
+    const int nblk = (D + kHeadBlock - 1) / kHeadBlock, items = ph.B * nblk;
+    for (int it = blockIdx.x; it < items; it += gridDim.x) {
+        const int b = it / nblk, d_lo = (it % nblk) * kHeadBlock, d_hi = min(D, d_lo + kHeadBlock);
+        __syncthreads();
+        if (warp == 0) {
+            const float* x = xs + (size_t)b * T * W;
+            float s = 0.f;
+            for (int c = lane; c < W; c += 32) { const float t = __ldcg(x + c); y[c] = t; s += t; }
+            const float mean = warp_sum(s) / W;
+            float qv = 0.f;
+            for (int c = lane; c < W; c += 32) { const float d = y[c] - mean; qv += d * d; }
+            const float rstd = rsqrtf(warp_sum(qv) / W + 1e-5f);
+            for (int c = lane; c < W; c += 32) y[c] = (y[c] - mean) * rstd * __ldg(gain + c) + __ldg(bias + c);
+        }
+        __syncthreads();
+        for (int d0 = d_lo + warp * 2; d0 < d_hi; d0 += nw * 2) {           // D is even: (d0, d0 + 1) stay inside the block
+            const float* w0 = projT + (size_t)d0 * W;
+            const float* w1 = w0 + W;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 2
+            for (int k = lane * 4; k < W; k += 128) {
+                const float4 yy = *reinterpret_cast<const float4*>(y + k);
+                const float4 c0 = __ldg(reinterpret_cast<const float4*>(w0 + k));
+                const float4 c1 = __ldg(reinterpret_cast<const float4*>(w1 + k));
+                a0 = fmaf(yy.x, c0.x, a0); a0 = fmaf(yy.y, c0.y, a0); a0 = fmaf(yy.z, c0.z, a0); a0 = fmaf(yy.w, c0.w, a0);
+                a1 = fmaf(yy.x, c1.x, a1); a1 = fmaf(yy.y, c1.y, a1); a1 = fmaf(yy.z, c1.z, a1); a1 = fmaf(yy.w, c1.w, a1);
+            }
+            a0 = warp_sum(a0); a1 = warp_sum(a1);
+            if (lane == 0) { raw[(size_t)b * D + d0] = a0; raw[(size_t)b * D + d0 + 1] = a1; }
         }
     }
 }
 
-// ln_post on the class token of every image: y[b] = LN(x[b*T]) (fp32)
-__device__ __forceinline__ void lnpost_phase(const Phase& ph)
-{
-    const int W = ph.W, lane = threadIdx.x & 31, wpb = blockDim.x >> 5, per = W / 32;
-    for (int b = blockIdx.x * wpb + (threadIdx.x >> 5); b < ph.B; b += gridDim.x * wpb) {
-        const float* x = ph.f1 + (size_t)b * ph.T * W;
-        float v[32];
-        float s = 0.f;
-        for (int i = 0; i < per; ++i) { v[i] = __ldcg(x + i * 32 + lane); s += v[i]; }
-        const float mean = warp_sum(s) / W;
-        float qv = 0.f;
-        for (int i = 0; i < per; ++i) { const float d = v[i] - mean; qv += d * d; }
-        const float rstd = rsqrtf(warp_sum(qv) / W + 1e-5f);
-        for (int i = 0; i < per; ++i) { const int c = i * 32 + lane; ph.f0[(size_t)b * W + c] = (v[i] - mean) * rstd * __ldg(ph.v0 + c) + __ldg(ph.v1 + c); }
-    }
-}
-
-// raw[b][d] = sum_k y[b][k] projT[d][k]: one warp per output element, fp32 FMA (B*D dot products of length W)
-__device__ __forceinline__ void proj_phase(const Phase& ph)
-{
-    const int W = ph.W, D = ph.D, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
-    const int total = ph.B * D;
-    for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < total; e += gridDim.x * wpb) {
-        const int b = e / D, d = e % D;
-        const float* y = ph.f1 + (size_t)b * W;
-        const float* w = ph.v0 + (size_t)d * W;
-        float acc = 0.f;
-        for (int k = lane * 4; k < W; k += 128) {
-            const float4 a = __ldcg(reinterpret_cast<const float4*>(y + k));
-            const float4 c = __ldg(reinterpret_cast<const float4*>(w + k));
-            acc = fmaf(a.x, c.x, acc); acc = fmaf(a.y, c.y, acc); acc = fmaf(a.z, c.z, acc); acc = fmaf(a.w, c.w, acc);
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) ph.f0[e] = acc;
-    }
-}
-
-// emb = raw / max(|raw|, 1e-12) (+ optional copy of raw, + hi/lo bf16 planes of emb for sc_cosine_topk)
+// head, part 2: emb = raw / max(|raw|, 1e-12) (+ optional copy of raw, + hi/lo bf16 planes of emb for sc_cosine_topk); one warp per image
 __device__ __forceinline__ void l2norm_phase(const Phase& ph, float* emb, float* raw_out, __nv_bfloat16* e_hi, __nv_bfloat16* e_lo)
 {
     const int D = ph.D, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -617,7 +738,7 @@ clip_tower_kernel(const Phase* __restrict__ phases, const CUtensorMap* __restric
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxStages; ++s) { mbar_init(sm.full + s, 1); mbar_init(sm.empty + s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(sm.tfull + b, 1); mbar_init(sm.tempty + b, 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(sm.tfull + b, 1); mbar_init(sm.tempty + b, 8); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(sm.tmem_slot);
@@ -637,8 +758,7 @@ clip_tower_kernel(const Phase* __restrict__ phases, const CUtensorMap* __restric
             case PH_ATTN:   attention_phase<SPLIT>(ph, sm.tiles); break;
             case PH_IM2COL: im2col_phase<SPLIT>(ph, ph.f1 != nullptr ? ph.f1 : images); break;
             case PH_TOKENS: tokens_phase<SPLIT>(ph); break;
-            case PH_LNPOST: lnpost_phase(ph); break;
-            case PH_PROJ:   proj_phase(ph); break;
+            case PH_HEAD:   head_phase(ph, reinterpret_cast<float*>(sm.tiles)); break;
             default:        l2norm_phase(ph, emb, raw_out, e_hi, e_lo); break;
         }
         if (p + 1 < ph_end) grid_sync(barrier_counter, target);
@@ -708,13 +828,13 @@ static Workspace carve(const ScClipConfig& c, int B, uint8_t* base) {
     return w;
 }
 
-// tile width for a GEMM of M x N on `ctas` persistent CTAs: the multiple of 16 dividing N (<= 256, >= 64) with the best
+// tile width for a GEMM of M x N on `ctas` persistent CTAs: the multiple of 32 dividing N (<= 256, >= 64) with the best
 // wave efficiency tiles / (ceil(tiles / ctas) * ctas), discounted when the MMA becomes shared-memory-read-bound (small N)
-static int choose_bn(int M, int N, int ctas, int max_bn) {
+static int choose_bn(int M, int N, int ctas, int max_bn, int step = 32) {
     const int MT = (M + 127) / 128;
     int best = 0;
     double best_e = -1.0;
-    for (int bn = max_bn; bn >= 64; bn -= 16) {
+    for (int bn = max_bn; bn >= 64; bn -= step) {
         if (N % bn) continue;
         const int tiles = MT * (N / bn);
         const int waves = (tiles + ctas - 1) / ctas;
@@ -736,7 +856,7 @@ extern "C" size_t sc_clip_tower_workspace_bytes(const ScClipConfig* cfg, int bat
 }
 extern "C" size_t sc_clip_tower_plan_bytes(const ScClipConfig* cfg) {
     if (cfg == nullptr) return 0;
-    const size_t n_phase = 3 + 5 * (size_t)cfg->layers + 3, n_maps = 8 + 2 * (4 * (size_t)cfg->layers + 1);
+    const size_t n_phase = 3 + 5 * (size_t)cfg->layers + 2, n_maps = 8 + 2 * (4 * (size_t)cfg->layers + 1);
     return align_up(n_phase * sizeof(Phase), 128) + n_maps * sizeof(CUtensorMap) + 128;
 }
 
@@ -761,7 +881,10 @@ extern "C" int sc_clip_tower_plan(const ScClipConfig* cfg, const ScClipTowerWeig
     if (cfg == nullptr || wts == nullptr || workspace == nullptr || plan == nullptr || batch <= 0) return (int)cudaErrorInvalidValue;
     const ScClipConfig& c = *cfg;
     const int G = c.image_size / c.patch, T = G * G + 1, W = c.width, H = c.heads, D = c.out_dim;
-    if (W % 64 != 0 || W > 1024 || W / H != 64 || (3 * c.patch * c.patch) % 2 != 0 || c.patch % 2 != 0) return (int)cudaErrorInvalidValue;
+    const int per = W / 32;
+    if (W % 128 != 0 || !(per == 4 || per == 8 || per == 16 || per == 24 || per == 32) || W / H != 64 || D % 2 != 0 ||
+        (3 * c.patch * c.patch) % 2 != 0 || c.patch % 2 != 0) return (int)cudaErrorInvalidValue;
+    if ((double)batch * G * G * ((3.0 * c.patch * c.patch + 63) / 64 * 64) > 2.0e9) return (int)cudaErrorInvalidValue;      // im2col indexes with 32 bits
     Workspace w = carve(c, batch, (uint8_t*)workspace);
     if (workspace_bytes < w.bytes || plan_bytes < sc_clip_tower_plan_bytes(cfg)) return (int)cudaErrorInvalidValue;
     const int Mp = batch * G * G, M = batch * T, Kp = (3 * c.patch * c.patch + 63) / 64 * 64;
@@ -772,7 +895,7 @@ extern "C" int sc_clip_tower_plan(const ScClipConfig* cfg, const ScClipTowerWeig
     cudaDeviceGetAttribute(&ctas, cudaDevAttrMultiProcessorCount, dev);
     const int max_bn = 256;
     // residual GEMMs (N = W) share ONE tile width: their (mean, M2) partials must line up with what the LN-folded consumers merge
-    const int bn_res = choose_bn(M, W, ctas, max_bn);
+    const int bn_res = choose_bn(M, W, ctas, max_bn, 64);        // halves of 32-column multiples: the token phase's statistics segments
     const int bn_qkv = choose_bn(M, 3 * W, ctas, max_bn), bn_fc1 = choose_bn(M, 4 * W, ctas, max_bn);
     const int bn_patch = choose_bn(Mp, W, ctas, max_bn);
     if (!bn_res || !bn_qkv || !bn_fc1 || !bn_patch) return (int)cudaErrorInvalidValue;
@@ -788,7 +911,9 @@ extern "C" int sc_clip_tower_plan(const ScClipConfig* cfg, const ScClipTowerWeig
         maps.push_back(m);
         return idx;
     };
-    auto zero_phase = [&]() { Phase p; memset(&p, 0, sizeof(p)); p.B = batch; p.H = H; p.W = W; p.P = c.patch; p.S = c.image_size; p.Kp = Kp; p.D = D; p.T = T; return p; };
+    const char* dbg_env = getenv("SC_TOWER_DEBUG");
+    const int dbg_flags = dbg_env ? atoi(dbg_env) : 0;        // diagnostics: 1 = skip residual read, 2 = skip fp32 store, 4 = skip 16-bit store (WRONG RESULTS)
+    auto zero_phase = [&]() { Phase p; memset(&p, 0, sizeof(p)); p.pad0 = dbg_flags; p.B = batch; p.H = H; p.W = W; p.P = c.patch; p.S = c.image_size; p.Kp = Kp; p.D = D; p.T = T; return p; };
     const int m_patch = add_map(w.patch[0], w.patch[1], Mp, Kp, 128);
     const int m_x = add_map(w.x16[0], w.x16[1], M, W, 128);
     const int m_attn = add_map(w.attn[0], w.attn[1], M, W, 128);
@@ -800,10 +925,10 @@ extern "C" int sc_clip_tower_plan(const ScClipConfig* cfg, const ScClipTowerWeig
         Phase p = zero_phase(); p.type = PH_IM2COL; p.o_hi = w.patch[0]; p.o_lo = w.patch[1]; ph.push_back(p);
         p = zero_phase(); p.type = PH_GEMM; p.M = Mp; p.N = W; p.K = Kp; p.BN = bn_patch; p.epi = EPI_F32; p.map_a = m_patch; p.map_w = m_conv;
         p.f0 = w.patch_out; ph.push_back(p);
-        p = zero_phase(); p.type = PH_TOKENS; p.M = M; p.BN = bn_res; p.v0 = wts->class_emb; p.v1 = wts->pos_emb; p.v2 = wts->lnpre_w; p.v3 = wts->lnpre_b;
+        p = zero_phase(); p.type = PH_TOKENS; p.M = M; p.v0 = wts->class_emb; p.v1 = wts->pos_emb; p.v2 = wts->lnpre_w; p.v3 = wts->lnpre_b;
         p.f0 = w.x; p.f1 = w.patch_out; p.o_hi = w.x16[0]; p.o_lo = w.x16[1]; p.st_out = w.st_a; ph.push_back(p);
     }
-    const int parts = W / bn_res;
+    const int parts = 2 * (W / bn_res), cnt = bn_res / 2;       // every residual tile leaves TWO (mean, M2) partials per row (its two epilogue column halves)
     for (int l = 0; l < c.layers; ++l) {
         const ScClipTowerLayer& L = wts->layers[l];
         const int m_qkv = add_map(L.qkv_w_hi, L.qkv_w_lo, 3 * W, W, bn_qkv);
@@ -813,7 +938,7 @@ extern "C" int sc_clip_tower_plan(const ScClipConfig* cfg, const ScClipTowerWeig
         if (m_qkv < 0 || m_out < 0 || m_fc1 < 0 || m_fc2 < 0) return (int)cudaErrorInvalidValue;
         Phase p = zero_phase();            // qkv = LN1(x) Wqkv^T + b   (q columns pre-scaled by 1/8)
         p.type = PH_GEMM; p.M = M; p.N = 3 * W; p.K = W; p.BN = bn_qkv; p.epi = EPI_LN16; p.map_a = m_x; p.map_w = m_qkv;
-        p.v0 = L.qkv_s; p.v1 = L.qkv_c; p.o_hi = w.qkv[0]; p.o_lo = w.qkv[1]; p.st_in = w.st_a; p.parts_in = parts; p.cnt_in = bn_res; ph.push_back(p);
+        p.v0 = L.qkv_s; p.v1 = L.qkv_c; p.o_hi = w.qkv[0]; p.o_lo = w.qkv[1]; p.st_in = w.st_a; p.parts_in = (l == 0) ? 1 : parts; p.cnt_in = (l == 0) ? W : cnt; ph.push_back(p);
         p = zero_phase();                  // attention
         p.type = PH_ATTN; p.i_hi = w.qkv[0]; p.i_lo = w.qkv[1]; p.o_hi = w.attn[0]; p.o_lo = w.attn[1]; ph.push_back(p);
         p = zero_phase();                  // x += attn Wo^T + bo ; statistics for LN2
@@ -821,14 +946,13 @@ extern "C" int sc_clip_tower_plan(const ScClipConfig* cfg, const ScClipTowerWeig
         p.v1 = L.out_b; p.f0 = w.x; p.o_hi = w.x16[0]; p.o_lo = w.x16[1]; p.st_out = w.st_b; ph.push_back(p);
         p = zero_phase();                  // h = QuickGELU(LN2(x) W1^T + b1)
         p.type = PH_GEMM; p.M = M; p.N = 4 * W; p.K = W; p.BN = bn_fc1; p.epi = EPI_LN16; p.act = 1; p.map_a = m_x; p.map_w = m_fc1;
-        p.v0 = L.fc1_s; p.v1 = L.fc1_c; p.o_hi = w.h[0]; p.o_lo = w.h[1]; p.st_in = w.st_b; p.parts_in = parts; p.cnt_in = bn_res; ph.push_back(p);
+        p.v0 = L.fc1_s; p.v1 = L.fc1_c; p.o_hi = w.h[0]; p.o_lo = w.h[1]; p.st_in = w.st_b; p.parts_in = parts; p.cnt_in = cnt; ph.push_back(p);
         p = zero_phase();                  // x += h W2^T + b2 ; statistics for the next layer's LN1
         p.type = PH_GEMM; p.M = M; p.N = W; p.K = 4 * W; p.BN = bn_res; p.epi = EPI_RESID; p.map_a = m_h; p.map_w = m_fc2;
         p.v1 = L.fc2_b; p.f0 = w.x; p.o_hi = w.x16[0]; p.o_lo = w.x16[1]; p.st_out = w.st_a; ph.push_back(p);
     }
     {
-        Phase p = zero_phase(); p.type = PH_LNPOST; p.v0 = wts->lnpost_w; p.v1 = wts->lnpost_b; p.f0 = w.y; p.f1 = w.x; ph.push_back(p);
-        p = zero_phase(); p.type = PH_PROJ; p.v0 = wts->proj_t; p.f0 = w.raw; p.f1 = w.y; ph.push_back(p);
+        Phase p = zero_phase(); p.type = PH_HEAD; p.v0 = wts->lnpost_w; p.v1 = wts->lnpost_b; p.v2 = wts->proj_t; p.f0 = w.raw; p.f1 = w.x; ph.push_back(p);
         p = zero_phase(); p.type = PH_L2NORM; p.f0 = w.raw; ph.push_back(p);
     }
     const size_t ph_bytes = align_up(ph.size() * sizeof(Phase), 128);
@@ -877,7 +1001,7 @@ extern "C" int sc_clip_tower_encode(const ScClipConfig* cfg, const void* plan, i
                                     float* emb, float* emb_unnormalised, void* emb_hi, void* emb_lo, int mode, cudaStream_t stream)
 {
     if (cfg == nullptr || plan == nullptr || workspace == nullptr || images == nullptr || n_phases <= 0) return (int)cudaErrorInvalidValue;
-    const size_t n_phase_cap = 3 + 5 * (size_t)cfg->layers + 3;
+    const size_t n_phase_cap = 3 + 5 * (size_t)cfg->layers + 2;
     const Phase* phases = reinterpret_cast<const Phase*>(plan);
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const uint8_t*>(plan) + align_up(n_phase_cap * sizeof(Phase), 128));
     unsigned* counter = reinterpret_cast<unsigned*>(workspace);

@@ -54,7 +54,7 @@ def test_encode_image_matches_oracle(name, B):
     img = torch.randn(B, 3, cfg["image_size"], cfg["image_size"])
     with torch.no_grad():
         want = clip_ref.encode_image(p, cfg, img)
-    vis = clip.CLIPVisual(name, precision="split")
+    vis = clip.CLIPVisual(name, precision="split_v1")          # the round-1 kernel chain; the tower: tests/test_clip_tower_gpu.py
     vis.load_params(p)
     vis = vis.cuda()
     raw, emb = vis.encode(img.cuda())
