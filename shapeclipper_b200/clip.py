@@ -264,10 +264,31 @@ class _Model:
         return self
 
 
-def preprocess(image_tensor, size=224):
-    """CLIP's image transform on a float tensor in [0,1] [..,3,h,w]: bicubic resize (short side), centre crop, normalise."""
+def preprocess(image, size=224):
+    """CLIP's image transform (openai/CLIP `_transform`: Resize(size, BICUBIC) on the shorter side -> CenterCrop(size) -> RGB ->
+    ToTensor -> Normalize(CLIP_MEAN, CLIP_STD)), the callable `clip.load` returns second and the reference hands to its dataset
+    (CLIP_anno.py:137-143, applied per image at data/pix3d.py:286-288).
+      * PIL.Image -> float32 CPU tensor [3, size, size]: PIL's own bicubic resize, so the result is bit-equal to torchvision's
+        Compose of the same steps (tests/test_clip_anno.py);
+      * float tensor in [0, 1], [..., 3, h, w] (any device) -> the same steps with torch's antialiased bicubic interpolation."""
+    if not isinstance(image, torch.Tensor):
+        import numpy as np
+        from PIL import Image
+        w, h = image.size
+        short, long_ = (w, h) if w <= h else (h, w)
+        if short != size:
+            new_short, new_long = size, int(size * long_ / short)
+            nw, nh = (new_short, new_long) if w <= h else (new_long, new_short)
+            image = image.resize((nw, nh), Image.BICUBIC)
+        w, h = image.size
+        top, left = int(round((h - size) / 2.0)), int(round((w - size) / 2.0))
+        image = image.crop((left, top, left + size, top + size)).convert("RGB")
+        x = torch.from_numpy(np.asarray(image, dtype=np.uint8).copy()).permute(2, 0, 1).float().div(255)
+        mean = torch.tensor(CLIP_MEAN).view(3, 1, 1)
+        std = torch.tensor(CLIP_STD).view(3, 1, 1)
+        return (x - mean) / std
     import torch.nn.functional as F
-    x = image_tensor
+    x = image
     h, w = x.shape[-2:]
     sc = size / min(h, w)
     nh, nw = max(size, round(h * sc)), max(size, round(w * sc))
@@ -288,7 +309,7 @@ def load(name="ViT-L/14", device="cuda", precision="split", state_dict=None):
 
 
 @torch.no_grad()
-def calc_matches(features, k_nearest=6, bank=None, thres=None):
+def calc_matches(features, k_nearest=6, bank=None, thres=None, query_tile_bytes=1 << 30):
     """Cosine k-NN of L2-normalised features [N,D] against themselves (or `bank`): (indices [N,k], values [N,k]).
     NN_annotator.calc_matches (CLIP_anno.py:29-57): one tcgen05 GEMM + one top-k kernel instead of N GEMVs.
     `thres` (opt.thres, CLIP_anno.py:42-54): rows with at least k-1 similarities in [thres, 1) return the query itself
@@ -300,44 +321,53 @@ def calc_matches(features, k_nearest=6, bank=None, thres=None):
     b = f if bank is None else bank.float().contiguous()
     N, D = f.shape
     Nb = b.shape[0]
+    if thres is not None and bank is not None:
+        raise ValueError("thres sampling is defined for the self-similarity case of the reference (no separate bank)")
     pad = (-Nb) % 64
     if pad:
         b = torch.cat([b, torch.zeros(pad, D, device=b.device)], 0)
     if D % 64:
         raise ValueError("embedding dim must be a multiple of 64")
-    q_hi, q_lo = split_bf16(f)
     b_hi, b_lo = split_bf16(b)
-    sim = torch.empty(N, b.shape[0], device=f.device)
     val = torch.empty(N, k_nearest, device=f.device)
-    idx = torch.empty(N, k_nearest, dtype=torch.int32, device=f.device)
-    with torch.cuda.device(f.device):
-        _lib.check(L.sc_cosine_topk(_p(q_hi), _p(q_lo), _p(b_hi), _p(b_lo), N, b.shape[0], Nb, D, k_nearest, _p(sim), _p(val),
-                                    _p(idx), _lib.stream_of(f)), "sc_cosine_topk")
+    idx = torch.empty(N, k_nearest, dtype=torch.long, device=f.device)
+    # queries in tiles: the fp32 similarity matrix is [tile, Nb], not [N, Nb] (the reference streams one query row at a time;
+    # at dataset scale N x N fp32 would be tens of GB)
+    tile = max(64, min(N, (query_tile_bytes // (4 * b.shape[0])) // 64 * 64))
+    sim = torch.empty(tile, b.shape[0], device=f.device)
     from . import _render_native as rn
-    rn.TIMERS.count(2)
-    idx = idx.long()
-    if thres is None:
-        return idx, val
-    if bank is not None:
-        raise ValueError("thres sampling is defined for the self-similarity case of the reference (no separate bank)")
-    s = sim[:, :Nb]
-    ok = (s >= thres) & (s < 1.)
-    counts = ok.sum(1).cpu()                                   # the only host round trip: the draws happen on the CPU generator
-    cols = ok.nonzero()[:, 1]                                  # row-major, ascending column inside a row (= .nonzero() per row)
-    starts = torch.cumsum(counts, 0) - counts
-    rows_i, rows_sel = [], []
-    for i in range(N):
-        n_valid = int(counts[i])
-        if n_valid < k_nearest - 1:
+    for q0 in range(0, N, tile):
+        q1 = min(N, q0 + tile)
+        n = q1 - q0
+        q_hi, q_lo = split_bf16(f[q0:q1])
+        v_t = torch.empty(n, k_nearest, device=f.device)
+        i_t = torch.empty(n, k_nearest, dtype=torch.int32, device=f.device)
+        with torch.cuda.device(f.device):
+            _lib.check(L.sc_cosine_topk(_p(q_hi), _p(q_lo), _p(b_hi), _p(b_lo), n, b.shape[0], Nb, D, k_nearest, _p(sim), _p(v_t),
+                                        _p(i_t), _lib.stream_of(f)), "sc_cosine_topk")
+        rn.TIMERS.count(2)
+        val[q0:q1], idx[q0:q1] = v_t, i_t.long()
+        if thres is None:
             continue
-        rows_i.append(i)
-        rows_sel.append(starts[i] + torch.randperm(n_valid)[:k_nearest - 1])
-    if rows_i:
-        ri = torch.tensor(rows_i, device=f.device)
-        sel = cols[torch.stack(rows_sel).to(f.device)]       # [n_rows, k-1]
-        full = torch.cat([ri.unsqueeze(1), sel], dim=1)
-        idx[ri] = full
-        val[ri] = torch.gather(s[ri], 1, full)
+        # opt.thres branch, rows of this tile in order: the draws come from the CPU generator exactly as in the reference's loop
+        s = sim[:n, :Nb]
+        ok = (s >= thres) & (s < 1.)
+        counts = ok.sum(1).cpu()                                   # one host round trip per tile
+        cols = ok.nonzero()[:, 1]                                  # row-major, ascending column inside a row (= .nonzero() per row)
+        starts = torch.cumsum(counts, 0) - counts
+        rows_i, rows_sel = [], []
+        for i in range(n):
+            n_valid = int(counts[i])
+            if n_valid < k_nearest - 1:
+                continue
+            rows_i.append(i)
+            rows_sel.append(starts[i] + torch.randperm(n_valid)[:k_nearest - 1])
+        if rows_i:
+            ri = torch.tensor(rows_i, device=f.device)
+            sel = cols[torch.stack(rows_sel).to(f.device)]       # [n_rows, k-1]
+            full = torch.cat([(ri + q0).unsqueeze(1), sel], dim=1)
+            idx[ri + q0] = full
+            val[ri + q0] = torch.gather(s[ri], 1, full)
     return idx, val
 
 

@@ -2,8 +2,9 @@
 
     import shapeclipper_b200.shim; shapeclipper_b200.shim.install()
 
-registers `model.renderer`, `model.implicit` and `chamfer_3D` in sys.modules before the reference imports them
-(model/graph.py:10-12, utils/eval_3D.py:6)."""
+registers `model.renderer`, `model.implicit`, `chamfer_3D` and `clip` in sys.modules before the reference imports them
+(model/graph.py:10-12, utils/eval_3D.py:6, CLIP_anno.py:7). `clip` is only registered when no real openai/CLIP package is
+importable (the reference's annotator then gets this package's image tower: `clip.load(name, device)` -> (model, preprocess))."""
 import sys
 
 
@@ -12,4 +13,9 @@ def install():
     sys.modules["model.renderer"] = renderer
     sys.modules["model.implicit"] = implicit
     sys.modules["chamfer_3D"] = chamfer_3D
+    if "clip" not in sys.modules:
+        import importlib.util
+        if importlib.util.find_spec("clip") is None:
+            from . import clip
+            sys.modules["clip"] = clip
     return renderer, implicit, chamfer_3D
