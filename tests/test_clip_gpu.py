@@ -106,3 +106,78 @@ def test_calc_matches_threshold_sampling_matches_oracle():
     assert (got_i[:200].cpu() == want_i[:200]).all()
     assert torch.allclose(got_v.cpu(), want_v, atol=2e-5)
     assert (got_i[200:].cpu() == want_i[200:]).float().mean() > 0.97       # top-k rows: near-ties may swap
+
+
+def test_calc_matches_matches_the_reference_functions_golden(golden_dir):
+    """tests/golden/calc_matches.pt holds NN_annotator.calc_matches' own output (CLIP_anno.py:29-57, generated from the live
+    reference): top-k branch and both sub-branches of the opt.thres branch with its CPU-generator randperm draws."""
+    import os
+    from shapeclipper_b200 import clip
+    fx = torch.load(os.path.join(golden_dir, "calc_matches.pt"), weights_only=False)
+    f = fx["features"].cuda()
+    idx, val = clip.calc_matches(f, 6)
+    assert torch.equal(idx.cpu(), fx["topk"]["indices"]) and torch.allclose(val.cpu(), fx["topk"]["values"], atol=2e-6)
+    for key in ("thres_0.55", "thres_0.895"):
+        c = fx[key]
+        s = fx["features"] @ fx["features"].t()
+        assert float((s - c["thres"]).abs().min()) > 1e-5          # no similarity sits on the threshold: the branch taken is robust
+        torch.manual_seed(c["seed"])
+        idx, val = clip.calc_matches(f, 6, thres=c["thres"])
+        sampled = (c["indices"] != fx["topk"]["indices"]).any(1)
+        assert torch.equal(idx.cpu()[sampled], c["indices"][sampled]), key
+        assert torch.allclose(val.cpu(), c["values"], atol=2e-6), key
+
+
+def test_calc_matches_query_tiling_changes_nothing():
+    from shapeclipper_b200 import clip
+    torch.manual_seed(6)
+    f = torch.nn.functional.normalize(torch.randn(700, 128), dim=-1).cuda()
+    i0, v0 = clip.calc_matches(f, 6)
+    i1, v1 = clip.calc_matches(f, 6, query_tile_bytes=64 * 704 * 4)            # 64-query tiles
+    assert torch.equal(i0, i1) and torch.equal(v0, v1)
+    torch.manual_seed(3)
+    a = clip.calc_matches(f, 6, thres=0.1)
+    torch.manual_seed(3)
+    b = clip.calc_matches(f, 6, thres=0.1, query_tile_bytes=64 * 704 * 4)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+
+
+def test_reference_annotator_runs_on_this_package_under_the_shim(tmp_path):
+    """CLIP_anno.py's own NN_annotator (clip.load('ViT-L/14') at :16, encode_image at :166, calc_matches, save_anno) with
+    shapeclipper_b200.shim.install() providing `clip`: its embeddings / neighbours / CSV equal this package's annotate()."""
+    import importlib
+    import sys
+    import numpy as np
+    import refharness
+    if not refharness.reference_available():
+        pytest.skip("reference modules not staged")
+    from PIL import Image
+    from shapeclipper_b200 import clip_anno, shim
+    sys.modules.pop("clip", None)
+    shim.install()
+    refharness.import_reference()
+    try:
+        import matplotlib  # noqa: F401
+    except Exception:
+        pass
+    anno = importlib.import_module("CLIP_anno")
+    import clip
+    assert clip.__name__ == "shapeclipper_b200.clip" and anno.clip is clip
+    opt = refharness.load_reference_opt()
+    opt.device, opt.thres, opt.anno_root = "cuda:0", None, str(tmp_path / "ref")
+    torch.manual_seed(0)
+    ann = anno.NN_annotator(opt)                                   # clip.load("ViT-L/14", device) -> this package's tower
+    ann.split = "train"
+    rng = np.random.RandomState(0)
+    images = [Image.fromarray(rng.randint(0, 256, size=(230 + 3 * i, 250, 3), dtype=np.uint8), "RGB") for i in range(9)]
+    labels = ["chair/%02d.png" % i for i in range(9)]
+    x = torch.stack([ann.preprocess(im) for im in images]).to(opt.device)                 # data/pix3d.py:286-288
+    feat = torch.nn.functional.normalize(ann.clip_encoder.encode_image(x).float(), dim=-1)      # CLIP_anno.py:166-167
+    ind, val = ann.calc_matches(opt, feat, k_nearest=6)                                        # the reference's per-query loop
+    ann.save_anno(opt, lambda root, label: (root + label if root == "" else root + "/" + label, None), labels, ind, val, k_nearest=6, category_set="custom")
+    path, idx, v = clip_anno.annotate(images, labels, str(tmp_path / "ours"), "chair", "train", model=ann.clip_encoder, k_nearest=6)
+    assert torch.equal(idx.cpu(), torch.stack(ind).cpu())
+    assert torch.allclose(v.cpu(), val.cpu(), atol=2e-5)
+    ours = open(path).read().splitlines()
+    ref = open(str(tmp_path / "ref" / "chair_train.csv")).read().splitlines()
+    assert ours[0] == ref[0] and [r.split(",")[:6] for r in ours] == [r.split(",")[:6] for r in ref]
