@@ -27,7 +27,7 @@ typedef struct CUstream_st* cudaStream_t;
 #endif
 
 /* ABI version of this header; bumped whenever a signature changes. */
-#define SC_B200_ABI_VERSION 2
+#define SC_B200_ABI_VERSION 3
 int sc_abi_version(void);
 
 /* ---- chamfer3D ------------------------------------------------------------
@@ -142,6 +142,10 @@ typedef struct ScRenderArgs {
      * needs (H, Q, FEAT, R, GPE planes + per-point vectors, 3.75 KB per sample point) are written to it. Backward: they are
      * read back instead of recomputing the forward per tile (19 of its 45 GEMM phases). NULL = recompute, no memory. */
     void* saved;
+    /* tensor-core kernels only. 0: every product is three MMAs on hi/lo bf16 operand pairs (fp32-class, the 1e-4 parity mode).
+     * 1: ONE MMA per product on the hi planes alone — plain bf16 operands with fp32 accumulation, the arithmetic BASELINE.json
+     * configs[2] names (about 1e-2 relative on rendered outputs); element-wise work (posenc, activations, compositing) stays fp32. */
+    int precision;
 } ScRenderArgs;
 
 size_t sc_render_blob_floats(void);

@@ -7,7 +7,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsc_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 _lib = None
 
 c_float_p = ctypes.c_void_p   # raw device addresses travel as void*

@@ -23,7 +23,7 @@ class ScRenderArgs(ctypes.Structure):
         ("rgb_bar", _fp), ("mask_bar", _fp), ("depth_bar", _fp), ("normal_bar", _fp), ("sdf_bar", _fp), ("grad_bar", _fp),
         ("grad_partial", _fp), ("cb_bar", _fp), ("ray_dirs_bar", _fp), ("depth_fac_bar", _fp), ("cam_loc_bar", _fp),
         ("scale_dist_bar", _fp), ("points_bar", _fp),
-        ("scratch", _fp), ("saved", _fp),
+        ("scratch", _fp), ("saved", _fp), ("precision", ctypes.c_int),
     ]
 
 

@@ -80,7 +80,7 @@ __device__ __forceinline__ void tc_init_tile_struct(TileTC& T, uint8_t* smem, co
     T.tid = threadIdx.x; T.lane = threadIdx.x & 31; T.warp = threadIdx.x >> 5;
     T.w0 = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0;          // warp-uniform for the compiler too
     T.wr.w0 = T.w0;
-    T.wide = true;
+    T.wide = true; T.single = false;
     T.row = 32 * (T.warp & 3) + T.lane; T.ch = T.warp >> 2;
 }
 
@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_fwd_kernel(const ScRend
 
     TileTC T;
     tc_init_tile_struct(T, smem, blob, seq, seq_len, 4, kWSlots);
+    if (a.precision == 1) { T.single = true; T.wide = false; }       // 64-column accumulators: nothing to add in the epilogue
     T.tmem = *tmem_slot;
     T.stash = stash_base + (size_t)blockIdx.x * TS_PLANES_FWD * kStashPlane;
     T.S = (MODE == 0) ? a.n_samples : 1;

@@ -317,6 +317,62 @@ SC_TC_ISSUE_FN void issue_wgrad(uint32_t tmem_d, const uint8_t* L, const uint8_t
         ::"r"(d), "r"(lh), "r"(ll), "r"(rh), "r"(rl), "r"(acc), "r"(kDescHi), "r"(idesc) : "memory");
 }
 
+// Single-MMA forms (ScRenderArgs::precision = 1, plain bf16 operands): the hi planes alone, 4 / 8 MMAs instead of 12 / 24.
+SC_TC_ISSUE_FN void issue_layer_gemm_single(uint32_t tmem_d, const uint8_t* act, const uint8_t* w, bool accumulate) {
+    constexpr uint32_t idesc = sctc::make_idesc_bf16(128, 64);
+    const uint32_t d = uniform_u32(tmem_d), acc = uniform_u32(accumulate ? 1u : 0u);
+    const uint32_t ah = desc_lo_k128(uniform_u32(sctc::smem_u32(act))), wh = desc_lo_k128(uniform_u32(sctc::smem_u32(w)));
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q, t;\n\t"
+        ".reg .b32 xa, ya;\n\t"
+        ".reg .b64 da, ea;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %3, 0;\n\t"
+        "setp.eq.u32 t, %3, %3;\n\t"
+        "add.u32 xa, %1, 0; add.u32 ya, %2, 0; mov.b64 da, {xa, %4}; mov.b64 ea, {ya, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %5, p;\n\t"
+        "add.u32 xa, %1, 2; add.u32 ya, %2, 2; mov.b64 da, {xa, %4}; mov.b64 ea, {ya, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %5, t;\n\t"
+        "add.u32 xa, %1, 4; add.u32 ya, %2, 4; mov.b64 da, {xa, %4}; mov.b64 ea, {ya, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %5, t;\n\t"
+        "add.u32 xa, %1, 6; add.u32 ya, %2, 6; mov.b64 da, {xa, %4}; mov.b64 ea, {ya, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %5, t;\n\t"
+        "}"
+        ::"r"(d), "r"(ah), "r"(wh), "r"(acc), "r"(kDescHi), "r"(idesc) : "memory");
+}
+SC_TC_ISSUE_FN void issue_wgrad_single(uint32_t tmem_d, const uint8_t* L, const uint8_t* R, bool accumulate) {
+    constexpr uint32_t idesc = make_idesc_bf16_mn(64, 64);
+    const uint32_t d = uniform_u32(tmem_d), acc = uniform_u32(accumulate ? 1u : 0u);
+    const uint32_t lh = desc_lo_mn128(uniform_u32(sctc::smem_u32(L))), rh = desc_lo_mn128(uniform_u32(sctc::smem_u32(R)));
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q, t;\n\t"
+        ".reg .b32 xa, ya;\n\t"
+        ".reg .b64 da, ea;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %3, 0;\n\t"
+        "setp.eq.u32 t, %3, %3;\n\t"
+        "add.u32 xa, %1, 0; add.u32 ya, %2, 0; mov.b64 da, {xa, %4}; mov.b64 ea, {ya, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %5, p;\n\t"
+        "add.u32 xa, %1, 128; add.u32 ya, %2, 128; mov.b64 da, {xa, %4}; mov.b64 ea, {ya, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %5, t;\n\t"
+        "add.u32 xa, %1, 256; add.u32 ya, %2, 256; mov.b64 da, {xa, %4}; mov.b64 ea, {ya, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %5, t;\n\t"
+        "add.u32 xa, %1, 384; add.u32 ya, %2, 384; mov.b64 da, {xa, %4}; mov.b64 ea, {ya, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %5, t;\n\t"
+        "add.u32 xa, %1, 512; add.u32 ya, %2, 512; mov.b64 da, {xa, %4}; mov.b64 ea, {ya, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %5, t;\n\t"
+        "add.u32 xa, %1, 640; add.u32 ya, %2, 640; mov.b64 da, {xa, %4}; mov.b64 ea, {ya, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %5, t;\n\t"
+        "add.u32 xa, %1, 768; add.u32 ya, %2, 768; mov.b64 da, {xa, %4}; mov.b64 ea, {ya, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %5, t;\n\t"
+        "add.u32 xa, %1, 896; add.u32 ya, %2, 896; mov.b64 da, {xa, %4}; mov.b64 ea, {ya, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, ea, %5, t;\n\t"
+        "}"
+        ::"r"(d), "r"(lh), "r"(rh), "r"(acc), "r"(kDescHi), "r"(idesc) : "memory");
+}
+
 // ---- weight ring: NS slots, TMA-filled (wfull), released by tcgen05.commit (wfree). Prefetch distance NS - 1:
 // a 16 KB bulk copy from L2 takes ~1-2 k cycles, longer than one tensor-core layer phase.
 struct WeightRing {

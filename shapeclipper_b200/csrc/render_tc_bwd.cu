@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
         T.w0 = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0;      // the issuing warp, warp-uniform for the compiler too
         T.wr.w0 = T.w0;
         T.wide = false;            // TMEM is full here (12 weight-gradient accumulators)
+        T.single = a.precision == 1;
         T.row = 32 * (T.warp & 3) + T.lane; T.ch = T.warp >> 2;
 #ifdef SC_TC_TRACE
         T.trace = (MODE == 0) ? reinterpret_cast<long long*>(a.points_bar) : nullptr; T.trace_n = 0;
@@ -151,7 +152,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
     const bool w0 = T.w0;
     uint32_t wg_init = 0;                 // issuing warp: which weight-gradient accumulators already hold data
     auto wgrad = [&](int m, const uint8_t* L, const uint8_t* R) {      // issuing warp only (all 32 lanes)
-        issue_wgrad(wg_taddr(T.tmem, m), L, R, (wg_init >> m) & 1u);
+        if (T.single) issue_wgrad_single(wg_taddr(T.tmem, m), L, R, (wg_init >> m) & 1u);
+        else issue_wgrad(wg_taddr(T.tmem, m), L, R, (wg_init >> m) & 1u);
         wg_init |= 1u << m;
     };
     // all threads: make the operand stores visible to the tensor core and line the CTA up (no weights involved)

@@ -17,6 +17,7 @@ struct TileTC {
     int tid, lane, warp, row, ch;
     bool w0;                    // member of the issuing warp (warp 0, warp-uniform)
     bool wide;                  // forward kernel: 128-column accumulators (issue_layer_gemm_wide); accumulator a lives at columns 2 a
+    bool single;                // ScRenderArgs::precision = 1: one MMA per product (hi planes only); never together with `wide`
     int b, first, S, rays_per_tile;
     float beta;
 #ifdef SC_TC_TRACE
@@ -62,6 +63,7 @@ struct TileTC {
         mark();
         if (w0) {
             if (wide) issue_layer_gemm_wide(tmem + 2 * acc_col, a, w, accumulate);
+            else if (single) issue_layer_gemm_single(tmem + acc_col, a, w, accumulate);
             else issue_layer_gemm(tmem + acc_col, a, w, accumulate);
             wr.release();
         }

@@ -11,12 +11,13 @@ _N_SDF, _N_RGB = 6, 4
 
 # Which generation of the render kernels runs: "tc2" / "tc" = tcgen05 tensor cores on hi/lo bf16 operand pairs (3 MMAs per
 # product, ~1e-5 relative; "tc2" = two independent 64-point tile chains per CTA, "tc" = one 128-point tile per CTA),
-# "fp32" = FP32 FFMA (the bit-for-bit-closest path). All are CUDA kernels of this library.
+# "bf16" = the "tc" kernels with ONE MMA per product on plain bf16 operands (ScRenderArgs.precision = 1; BASELINE.json
+# configs[2]'s arithmetic, ~1e-2 relative), "fp32" = FP32 FFMA (the bit-for-bit-closest path). All are CUDA kernels of this library.
 import os as _os
 PRECISION = {"forward": _os.environ.get("SC_RENDER_FORWARD", "tc"), "backward": _os.environ.get("SC_RENDER_BACKWARD", "tc")}
 
 
-STEP_PRECISIONS = ("tc",)          # render arithmetic modes bench.py's configs[2] record steps through
+STEP_PRECISIONS = ("tc", "bf16")   # render arithmetic modes bench.py's configs[2] record steps through
 
 
 SAVE_ACTIVATIONS = _os.environ.get("SC_RENDER_SAVE_ACTIVATIONS", "1") != "0"
@@ -25,18 +26,25 @@ SAVE_ACTIVATIONS = _os.environ.get("SC_RENDER_SAVE_ACTIVATIONS", "1") != "0"
 def set_precision(forward=None, backward=None):
     for k, v in (("forward", forward), ("backward", backward)):
         if v is not None:
-            if v not in ("tc2", "tc", "fp32"):
-                raise ValueError("precision must be 'tc2', 'tc' or 'fp32'")
+            if v not in ("tc2", "tc", "bf16", "fp32"):
+                raise ValueError("precision must be 'tc2', 'tc', 'bf16' or 'fp32'")
             PRECISION[k] = v
 
 
 def _fwd_tc():
-    """False (FP32 FFMA) or the tensor-core generation name ("tc" / "tc2", both truthy)."""
-    return PRECISION["forward"] if PRECISION["forward"] in ("tc", "tc2") else False
+    """False (FP32 FFMA) or the tensor-core generation name ("tc" / "tc2", both truthy); "bf16" runs the "tc" generation."""
+    p = PRECISION["forward"]
+    return ("tc" if p == "bf16" else p) if p in ("tc", "tc2", "bf16") else False
 
 
 def _bwd_tc():
-    return PRECISION["backward"] if PRECISION["backward"] in ("tc", "tc2") else False
+    p = PRECISION["backward"]
+    return ("tc" if p == "bf16" else p) if p in ("tc", "tc2", "bf16") else False
+
+
+def _single(direction):
+    """ScRenderArgs.precision: 1 = one MMA per product (plain bf16 operands), 0 = three (hi/lo pairs)."""
+    return 1 if PRECISION[direction] == "bf16" else 0
 
 
 def _params_of(sdf_net, rgb_net, device):
@@ -135,7 +143,8 @@ class _RenderFn(torch.autograd.Function):
                          cam_dist=cfg["cam_dist"], half_range=cfg["half_range"], bg_color=cfg["bg_color"],
                          normal_pow=cfg["normal_pow"], blob=kblob, cb=cb, beta_param=beta_c, cam_loc=cam_loc,
                          ray_dirs=ray_dirs, depth_fac=depth_fac, scale_dist=scale_dist, t_vals=t_vals,
-                         rgb=rgb, mask=mask, mask_hard=mask_hard, depth=depth, normal=normal, scratch=scratch)
+                         rgb=rgb, mask=mask, mask_hard=mask_hard, depth=depth, normal=normal, scratch=scratch,
+                         precision=_single("forward"))
         if jit is not None:
             args.jitter = ctypes.c_void_p(jit.data_ptr())
         # generation-1 tensor-core kernels, some input needs a gradient: the forward saves its per-point activations
@@ -184,7 +193,7 @@ class _RenderFn(torch.autograd.Function):
                          normal_pow=cfg["normal_pow"], blob=kblob, cb=cb, beta_param=beta_c, cam_loc=cam_loc,
                          ray_dirs=ray_dirs, depth_fac=depth_fac, scale_dist=scale_dist, t_vals=t_vals,
                          grad_partial=partial, cb_bar=cb_bar, ray_dirs_bar=dirs_bar, depth_fac_bar=fac_bar,
-                         cam_loc_bar=loc_bar, scale_dist_bar=sd_bar, scratch=scratch)
+                         cam_loc_bar=loc_bar, scale_dist_bar=sd_bar, scratch=scratch, precision=_single("backward"))
         if ctx.has_jitter:
             args.jitter = ctypes.c_void_p(jit.data_ptr())
         for name, t in (("rgb_bar", rgb_bar), ("mask_bar", mask_bar), ("depth_bar", depth_bar), ("normal_bar", normal_bar)):
@@ -223,7 +232,7 @@ class _SDFQueryFn(torch.autograd.Function):
         scratch = rn.scratch(dev, backward=False, tc=tc)
         kblob = rn.packed_tc_blob(ws, bs, blob) if tc else blob
         args = _new_args(mode=1, batch=B, n_per_image=N, n_samples=1, want_grad=int(want_grad), want_feat=1,
-                         beta_min=1e-4, blob=kblob, cb=cb, points=pts, sdf=sdf, feat=feat, scratch=scratch)
+                         beta_min=1e-4, blob=kblob, cb=cb, points=pts, sdf=sdf, feat=feat, scratch=scratch, precision=_single("forward"))
         if grad is not None:
             args.grad = ctypes.c_void_p(grad.data_ptr())
         rn.launch_forward(args, dev, tc=tc)
@@ -256,7 +265,7 @@ class _SDFQueryFn(torch.autograd.Function):
         kblob = rn.packed_tc_blob(ws, bs, blob) if tc else blob
         args = _new_args(mode=1, batch=B, n_per_image=N, n_samples=1, want_grad=int(want_grad and grad_bar is not None),
                          want_feat=0, detach_latent=int(detach_latent), beta_min=1e-4, blob=kblob, cb=cb, points=pts,
-                         grad_partial=partial, cb_bar=cb_bar, points_bar=pts_bar, scratch=scratch)
+                         grad_partial=partial, cb_bar=cb_bar, points_bar=pts_bar, scratch=scratch, precision=_single("backward"))
         if sdf_bar is not None:
             keep1 = rn._f32c(sdf_bar)
             args.sdf_bar = ctypes.c_void_p(keep1.data_ptr())
