@@ -289,7 +289,7 @@ def measure_train_step(a, opt, batch_size, steps, warmup, rank, world, dev, clip
     clip_ctx = None
     if clip:
         from shapeclipper_b200 import clip as scclip
-        clip_ctx = scclip.bench_context(opt, batch_size, dev)
+        clip_ctx = scclip.bench_context(opt, batch_size, dev, precision=os.environ.get("SC_BENCH_CLIP", "split"))
     batches = [synthetic.make_batch(opt, batch_size, seed=1000 * rank + i) for i in range(n_batches)]
     resident = [{k: t.to(dev) for k, t in b.items()} for b in batches]
     h2d_bytes = sum(t.numel() * t.element_size() for t in batches[0].values())

@@ -85,7 +85,9 @@ __device__ __forceinline__ void tc_init_tile_struct(TileTC& T, uint8_t* smem, co
 }
 
 // SAVE (mode 0 only): a.saved receives every tile's activation planes + per-point vectors for sc_render_tc_backward
-template <int MODE, bool SAVE>
+// PREC (ScRenderArgs::precision) is a TEMPLATE parameter: the single-MMA mode as a run-time branch in the issue path made the
+// default (split) kernels 6 % slower (instruction-cache footprint of the issuing warp).
+template <int MODE, bool SAVE, int PREC>
 __global__ void __launch_bounds__(kThreads, 1) render_tc_fwd_kernel(const ScRenderArgs a, float* stash_base)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_fwd_kernel(const ScRend
 
     TileTC T;
     tc_init_tile_struct(T, smem, blob, seq, seq_len, 4, kWSlots);
-    if (a.precision == 1) { T.single = true; T.wide = false; }       // 64-column accumulators: nothing to add in the epilogue
+    if (PREC == 1) { T.single = true; T.wide = false; }              // 64-column accumulators: nothing to add in the epilogue
     T.tmem = *tmem_slot;
     T.stash = stash_base + (size_t)blockIdx.x * TS_PLANES_FWD * kStashPlane;
     T.S = (MODE == 0) ? a.n_samples : 1;
@@ -264,18 +266,14 @@ extern "C" int sc_render_tc_forward(const ScRenderArgs* a, cudaStream_t stream)
     const long total = (long)a->batch * ((a->n_per_image + per_tile - 1) / per_tile);
     const int grid = total < sms ? (int)total : sms;
     cudaError_t err;
-    if (a->mode == 0 && a->saved != nullptr) {
-        err = cudaFuncSetAttribute(render_tc_fwd_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc);
-        if (err != cudaSuccess) return (int)err;
-        render_tc_fwd_kernel<0, true><<<grid, kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch);
-    } else if (a->mode == 0) {
-        err = cudaFuncSetAttribute(render_tc_fwd_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc);
-        if (err != cudaSuccess) return (int)err;
-        render_tc_fwd_kernel<0, false><<<grid, kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch);
-    } else {
-        err = cudaFuncSetAttribute(render_tc_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc);
-        if (err != cudaSuccess) return (int)err;
-        render_tc_fwd_kernel<1, false><<<grid, kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch);
-    }
+#define SC_LAUNCH_FWD(MODE_, SAVE_, PREC_) do { \
+        err = cudaFuncSetAttribute(render_tc_fwd_kernel<MODE_, SAVE_, PREC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc); \
+        if (err != cudaSuccess) return (int)err; \
+        render_tc_fwd_kernel<MODE_, SAVE_, PREC_><<<grid, kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch); } while (0)
+    const bool single = a->precision == 1;
+    if (a->mode == 0 && a->saved != nullptr) { if (single) SC_LAUNCH_FWD(0, true, 1); else SC_LAUNCH_FWD(0, true, 0); }
+    else if (a->mode == 0) { if (single) SC_LAUNCH_FWD(0, false, 1); else SC_LAUNCH_FWD(0, false, 0); }
+    else { if (single) SC_LAUNCH_FWD(1, false, 1); else SC_LAUNCH_FWD(1, false, 0); }
+#undef SC_LAUNCH_FWD
     return (int)cudaGetLastError();
 }

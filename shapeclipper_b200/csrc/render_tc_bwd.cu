@@ -87,7 +87,7 @@ __device__ __forceinline__ void fold_pe_tc(const TileTC& T, const float (&v)[NC]
     }
 }
 
-template <int MODE>
+template <int MODE, int PREC>      // PREC = ScRenderArgs::precision, compile-time (see render_tc.cu)
 __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRenderArgs a, float* stash_base)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
         T.w0 = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0;      // the issuing warp, warp-uniform for the compiler too
         T.wr.w0 = T.w0;
         T.wide = false;            // TMEM is full here (12 weight-gradient accumulators)
-        T.single = a.precision == 1;
+        T.single = (PREC == 1);
         T.row = 32 * (T.warp & 3) + T.lane; T.ch = T.warp >> 2;
 #ifdef SC_TC_TRACE
         T.trace = (MODE == 0) ? reinterpret_cast<long long*>(a.points_bar) : nullptr; T.trace_n = 0;
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
     const bool w0 = T.w0;
     uint32_t wg_init = 0;                 // issuing warp: which weight-gradient accumulators already hold data
     auto wgrad = [&](int m, const uint8_t* L, const uint8_t* R) {      // issuing warp only (all 32 lanes)
-        if (T.single) issue_wgrad_single(wg_taddr(T.tmem, m), L, R, (wg_init >> m) & 1u);
+        if (PREC == 1) issue_wgrad_single(wg_taddr(T.tmem, m), L, R, (wg_init >> m) & 1u);
         else issue_wgrad(wg_taddr(T.tmem, m), L, R, (wg_init >> m) & 1u);
         wg_init |= 1u << m;
     };
@@ -490,14 +490,13 @@ extern "C" int sc_render_tc_backward(const ScRenderArgs* a, cudaStream_t stream)
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t err;
-    if (a->mode == 0) {
-        err = cudaFuncSetAttribute(render_tc_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc);
-        if (err != cudaSuccess) return (int)err;
-        render_tc_bwd_kernel<0><<<sms, sct::kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch);
-    } else {
-        err = cudaFuncSetAttribute(render_tc_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc);
-        if (err != cudaSuccess) return (int)err;
-        render_tc_bwd_kernel<1><<<sms, sct::kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch);
-    }
+#define SC_LAUNCH_BWD(MODE_, PREC_) do { \
+        err = cudaFuncSetAttribute(render_tc_bwd_kernel<MODE_, PREC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc); \
+        if (err != cudaSuccess) return (int)err; \
+        render_tc_bwd_kernel<MODE_, PREC_><<<sms, sct::kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch); } while (0)
+    const bool single = a->precision == 1;
+    if (a->mode == 0) { if (single) SC_LAUNCH_BWD(0, 1); else SC_LAUNCH_BWD(0, 0); }
+    else { if (single) SC_LAUNCH_BWD(1, 1); else SC_LAUNCH_BWD(1, 0); }
+#undef SC_LAUNCH_BWD
     return (int)cudaGetLastError();
 }
