@@ -272,6 +272,23 @@ int sc_clip_tower_workspace_layout(const ScClipConfig* cfg, int batch, size_t* o
 int sc_clip_tower_encode(const ScClipConfig* cfg, const void* plan, int n_phases, void* workspace, const float* images,
                          float* emb, float* emb_unnormalised, void* emb_hi, void* emb_lo, int mode, cudaStream_t stream);
 
+/* ---- iso-surface extraction + surface sampling (csrc/mcubes.cu) ---------------------------------
+ * Replaces the CPU leg of utils/eval_3D.py:123-153: mcubes.marching_cubes(level, isovalue) + trimesh.Trimesh(..).sample(n)
+ * (both third-party, absent: tables generated from the definition, sampler restated from trimesh's published algorithm).
+ * level [B, n, n, n] fp32 device ([b][ix][iy][iz]); a lattice point is inside when level < isovalue.
+ *   sc_mc_set_tables : the case tables of shapeclipper_b200/mcubes_tables.py (HOST pointers), once per device
+ *   sc_mc_count      : counts [B * (n-1)^3] int32 = triangles per cell (cell id = ((b (n-1) + x)(n-1) + y)(n-1) + z)
+ *   sc_mc_emit       : offsets = exclusive scan of counts (int64); triangles [total, 3, 3] in world units, vertex = index / n *
+ *                      (hi - lo) + lo as the reference scales them (utils/eval_3D.py:136-140)
+ *   sc_tri_area      : area [n_tris]
+ *   sc_tri_sample    : points[i] = uniform point of triangle face[i] from the two uniforms uv[i] (folded when r1 + r2 > 1) */
+int sc_mc_set_tables(const int8_t* tri_count, const int8_t* tri_edges, const int8_t* edge_corner);
+int sc_mc_count(const float* level, int batch, int n, float isovalue, int32_t* counts, cudaStream_t stream);
+int sc_mc_emit(const float* level, int batch, int n, float isovalue, const int64_t* offsets, float lo, float hi, float* triangles,
+               cudaStream_t stream);
+int sc_tri_area(const float* triangles, int64_t n_tris, float* area, cudaStream_t stream);
+int sc_tri_sample(const float* triangles, const int64_t* face, const float* uv, int64_t count, float* points, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,9 +59,10 @@ def _declare(L):
     L.sc_render_losses_pass1.restype = i
     L.sc_render_losses_pass2.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, f, d, f, vp, vp, vp, vp, vp, vp]
     L.sc_render_losses_pass2.restype = i
-    from . import _render_native, clip
+    from . import _render_native, clip, mcubes
     _render_native.declare(L)
     clip.declare(L)
+    mcubes.declare(L)
 
 
 def ptr(t):

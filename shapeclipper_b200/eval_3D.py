@@ -1,10 +1,11 @@
-"""3-D evaluation pieces on the GPU path, with the reference's function names (utils/eval_3D.py):
-get_dense_3D_grid (9-18), compute_level_grid (21-38), normalize_pc (40-49), compute_fscore (105-121),
-chamfer_distance (155-165). Marching cubes + mesh sampling (convert_to_explicit, 123-153) are CPU third-party code
-(PyMCubes, trimesh) and stay outside: eval_metrics takes the predicted point cloud from a caller-supplied sampler."""
+"""The 3-D evaluation on the GPU path, with the reference's function names (utils/eval_3D.py): get_dense_3D_grid (9-18),
+compute_level_grid (21-38), normalize_pc (40-49), eval_metrics (52-103), compute_fscore (105-121), convert_to_explicit (123-153),
+chamfer_distance (155-165). The reference copies the level grid to the host, runs PyMCubes + trimesh on Python threads and copies
+the point clouds back; here iso-surface extraction and surface sampling are CUDA kernels (mcubes.py, csrc/mcubes.cu) and nothing
+leaves the device between the SDF queries and the F-score."""
 import torch
 
-from . import chamfer_3D
+from . import chamfer_3D, mcubes
 
 
 @torch.no_grad()
@@ -56,14 +57,43 @@ def chamfer_distance(opt, X1, X2):
     return d1.sqrt(), d2.sqrt(), i1, i2
 
 
+class Mesh:
+    """What convert_to_explicit hands back per shape (the reference returns trimesh.Trimesh objects): a device-resident
+    triangle soup with the two members the reference reads, `.triangles` and `.sample(count)`."""
+
+    def __init__(self, triangles):
+        self.triangles = triangles                       # [T, 3, 3] CUDA
+
+    def sample(self, count, generator=None):
+        return mcubes.sample_surface(self.triangles, int(count), generator)
+
+
 @torch.no_grad()
-def eval_metrics(opt, var, sdf_network, surface_sampler, vis_only=False):
-    """utils/eval_3D.py:52-103 with the mesh extraction injected: surface_sampler(level_vox [B,n,n,n]) -> [B,P,3]."""
+def convert_to_explicit(opt, level_grids, isoval=0., to_pointcloud=False, generator=None):
+    """utils/eval_3D.py:123-153: level grids [B,n,n,n] (tensor, or the reference's list of [n,n,n] arrays) -> meshes (and
+    [B, opt.eval.num_points, 3] surface samples). Vertices = index / n * (range_max - range_min) + range_min, n = grid points per
+    axis, exactly as the reference rescales PyMCubes' index-space vertices (:136-140); an empty mesh samples to zeros (:150-152)."""
+    if not isinstance(level_grids, torch.Tensor):
+        level_grids = torch.stack([torch.as_tensor(g, dtype=torch.float32) for g in level_grids]).to(opt.device)
+    lo, hi = opt.eval.range
+    meshes = [Mesh(t) for t in mcubes.extract_triangles(level_grids, isoval, lo=lo, hi=hi)]
+    if not to_pointcloud:
+        return meshes
+    return meshes, torch.stack([m.sample(opt.eval.num_points, generator) for m in meshes], 0)
+
+
+@torch.no_grad()
+def eval_metrics(opt, var, sdf_network, vis_only=False, surface_sampler=None, generator=None):
+    """utils/eval_3D.py:52-103. `surface_sampler(level_vox [B,n,n,n]) -> [B,P,3]` overrides the built-in GPU extraction + sampling
+    (tests inject analytic clouds through it); `generator` (CUDA) seeds the surface samples."""
     pts = get_dense_3D_grid(opt, var)
     B = pts.shape[0]
     level = compute_level_grid(opt, sdf_network, var.proj_latent_sdf, pts)
     var.eval_vox = pts.reshape(B, -1, 3)
-    var.dpc_pred = surface_sampler(level).to(pts.device).float()
+    if surface_sampler is not None:
+        var.dpc_pred = surface_sampler(level).to(pts.device).float()
+    else:
+        var.mesh_pred, var.dpc_pred = convert_to_explicit(opt, level, isoval=0., to_pointcloud=True, generator=generator)
     R_pred, R_gt = var.pose[..., :3], var.pose_gt[..., :3]
     pred = (R_pred @ var.dpc_pred.transpose(1, 2)).transpose(1, 2)
     gt = (R_gt @ var.dpc.points.transpose(1, 2)).transpose(1, 2)

@@ -2,9 +2,10 @@
 
     import shapeclipper_b200.shim; shapeclipper_b200.shim.install()
 
-registers `model.renderer`, `model.implicit`, `chamfer_3D` and `clip` in sys.modules before the reference imports them
-(model/graph.py:10-12, utils/eval_3D.py:6, CLIP_anno.py:7). `clip` is only registered when no real openai/CLIP package is
-importable (the reference's annotator then gets this package's image tower: `clip.load(name, device)` -> (model, preprocess))."""
+registers `model.renderer`, `model.implicit`, `chamfer_3D`, `clip`, `mcubes` and `trimesh` in sys.modules before the reference
+imports them (model/graph.py:10-12, utils/eval_3D.py:4-6, CLIP_anno.py:7). The three third-party names are only registered when
+the real packages are not importable (or are empty test stubs): the reference's annotator then gets this package's image tower
+(`clip.load(name, device)` -> (model, preprocess)) and its evaluation this package's GPU marching cubes / surface sampler."""
 import sys
 
 
@@ -13,9 +14,21 @@ def install():
     sys.modules["model.renderer"] = renderer
     sys.modules["model.implicit"] = implicit
     sys.modules["chamfer_3D"] = chamfer_3D
-    if "clip" not in sys.modules:
-        import importlib.util
-        if importlib.util.find_spec("clip") is None:
-            from . import clip
-            sys.modules["clip"] = clip
+    import importlib.util
+
+    def absent(name):
+        m = sys.modules.get(name)
+        if m is not None:
+            return getattr(m, "__file__", None) is None and not hasattr(m, "__path__") and not getattr(m, "__name__", "").startswith("shapeclipper_b200")
+        try:
+            return importlib.util.find_spec(name) is None
+        except (ValueError, ImportError):
+            return True
+    if absent("clip"):
+        from . import clip
+        sys.modules["clip"] = clip
+    if absent("mcubes") and absent("trimesh"):       # PyMCubes + trimesh (utils/eval_3D.py:4-5): GPU marching cubes + surface sampling
+        from . import mcubes
+        sys.modules["mcubes"] = mcubes
+        sys.modules["trimesh"] = mcubes
     return renderer, implicit, chamfer_3D
