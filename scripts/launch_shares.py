@@ -26,7 +26,7 @@ def main(path):
         a[0] += 1
         a[1] += ns
         total += ns
-    steps = sum(n for k, (n, _) in agg.items() if "render_tc_bwd_kernel<(int)0>" in k or "render_tc_bwd_kernel<0>" in k) / 2.0
+    steps = sum(n for k, (n, _) in agg.items() if "render_tc_bwd_kernel<(int)0" in k or "render_tc_bwd_kernel<0" in k) / 2.0
     print("# %d launches from the first render launch on, %.1f ms of kernel time, %.1f training steps (2 render backward launches each)"
           % (len(rows), total / 1e6, steps))
     print("# kernel, launches, launches/step, total_ns, share")
