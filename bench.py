@@ -289,7 +289,10 @@ def measure_train_step(a, opt, batch_size, steps, warmup, rank, world, dev, clip
     clip_ctx = None
     if clip:
         from shapeclipper_b200 import clip as scclip
-        clip_ctx = scclip.bench_context(opt, batch_size, dev, precision=os.environ.get("SC_BENCH_CLIP", "split"))
+        # inside the step the tower runs as cooperative launches of 2 phases each: ~0.1 ms pieces that the render stream's kernels
+        # interleave with (one 1.6-3 ms cooperative launch holds every SM; measured 12.31 -> 12.01 ms/step at batch 32)
+        clip_ctx = scclip.bench_context(opt, batch_size, dev, precision=os.environ.get("SC_BENCH_CLIP", "split"),
+                                        launch_group=int(os.environ.get("SC_TOWER_GROUP", "2")) if not a.no_side_stream else 0)
     batches = [synthetic.make_batch(opt, batch_size, seed=1000 * rank + i) for i in range(n_batches)]
     resident = [{k: t.to(dev) for k, t in b.items()} for b in batches]
     h2d_bytes = sum(t.numel() * t.element_size() for t in batches[0].values())

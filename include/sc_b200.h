@@ -268,7 +268,8 @@ int sc_clip_tower_plan(const ScClipConfig* cfg, const ScClipTowerWeights* weight
  * patch_out fp32, y fp32, raw fp32, stats a, stats b}. */
 int sc_clip_tower_workspace_layout(const ScClipConfig* cfg, int batch, size_t* offsets16);
 /* mode 0: one cooperative launch (+ one 4-byte memset); mode 1: one launch per phase (profiling form, same device code);
- * mode k >= 2: per-phase launches of the first k - 1 phases only (diagnostics). */
+ * mode k >= 2: per-phase launches of the first k - 1 phases only (diagnostics); mode -g (g > 0): cooperative launches of g phases
+ * each, the three embedding phases first (a tower that another stream's kernels can interleave with). */
 int sc_clip_tower_encode(const ScClipConfig* cfg, const void* plan, int n_phases, void* workspace, const float* images,
                          float* emb, float* emb_unnormalised, void* emb_hi, void* emb_lo, int mode, cudaStream_t stream);
 

@@ -104,6 +104,7 @@ class CLIPVisual(torch.nn.Module):
         self.cfg = dict(CONFIGS[name])
         self.precision = precision
         self.per_phase_launches = False          # tower engine: one ordinary launch per phase instead of one cooperative launch
+        self.launch_group = 0                    # tower engine, > 0: cooperative launches of that many phases each (pieces other streams' kernels interleave with)
         self._tower = None                       # (TowerWeights, cfg struct, {batch: TowerPlan})
         W, P, Ln = self.cfg["width"], self.cfg["patch"], self.cfg["layers"]
         T = (self.cfg["image_size"] // P) ** 2 + 1
@@ -229,7 +230,7 @@ class CLIPVisual(torch.nn.Module):
             hi = torch.empty(B, D, device=dev, dtype=torch.bfloat16) if want_planes else None
             lo = torch.empty(B, D, device=dev, dtype=torch.bfloat16) if want_planes else None
             with rn.TIMERS.span("clip_encode", dev):
-                n = _tower.encode(cfg, plan, img, emb, raw, hi, lo, per_phase_launches=self.per_phase_launches)
+                n = _tower.encode(cfg, plan, img, emb, raw, hi, lo, per_phase_launches=self.per_phase_launches, group=self.launch_group)
             rn.TIMERS.count(n)
             return (raw, emb, hi, lo) if want_planes else (raw, emb)
         cfg, w, _layers, _keep, dev = self._pack()
@@ -374,9 +375,13 @@ def calc_matches(features, k_nearest=6, bank=None, thres=None, query_tile_bytes=
 class _BenchContext:
     """CLIP leg of bench.py: encode the batch images (ViT-B/32, random init) and look up the 6 nearest of a 4096 bank."""
 
-    def __init__(self, opt, batch, device, bank_size=4096, precision="split"):
+    def __init__(self, opt, batch, device, bank_size=4096, precision="split", launch_group=0):
         self.model = CLIPVisual("ViT-B/32", precision=precision).to(device)
-        self.launches = (2 if precision in TOWER_PRECISIONS else 5 + 7 * self.model.cfg["layers"] + 3) + 2
+        if launch_group and precision in TOWER_PRECISIONS:
+            self.model.launch_group = int(launch_group)
+        g = self.model.launch_group
+        tower = 2 if not g else 2 * (1 + -(-(3 + 5 * self.model.cfg["layers"] - 1) // g))       # (memset + cooperative launch) per group of phases
+        self.launches = (tower if precision in TOWER_PRECISIONS else 5 + 7 * self.model.cfg["layers"] + 3) + 2
         self.device = device
         g = torch.Generator().manual_seed(7)
         self.host_images = [torch.randn(batch, 3, 224, 224, generator=g).pin_memory() for _ in range(2)]
@@ -405,5 +410,5 @@ class _BenchContext:
         return self.idx
 
 
-def bench_context(opt, batch, device, precision="split"):
-    return _BenchContext(opt, batch, device, precision=precision)
+def bench_context(opt, batch, device, precision="split", launch_group=0):
+    return _BenchContext(opt, batch, device, precision=precision, launch_group=launch_group)

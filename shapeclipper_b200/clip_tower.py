@@ -141,13 +141,17 @@ def workspace_layout(cfg_struct, batch):
     return dict(zip(LAYOUT_NAMES, [int(v) for v in arr]))
 
 
-def encode(cfg_struct, plan, images, emb, raw, hi, lo, per_phase_launches=False, stop_after=None):
+def encode(cfg_struct, plan, images, emb, raw, hi, lo, per_phase_launches=False, stop_after=None, group=0):
     """One tower encode on the current stream of images' device (1 memset + 1 cooperative launch; per_phase_launches=True
-    runs the same device code as one ordinary launch per phase — what ncu attributes GEMM by GEMM)."""
+    runs the same device code as one ordinary launch per phase — what ncu attributes GEMM by GEMM; group = g > 0: cooperative
+    launches of g phases each, for a tower that shares the GPU with another stream's kernels). Returns the number of launches."""
     L = _lib.lib()
     with torch.cuda.device(images.device):
         _lib.check(L.sc_clip_tower_encode(ctypes.byref(cfg_struct), _p(plan.plan), plan.n_phases, _p(plan.workspace), _p(images),
                                           _p(emb), _p(raw), _p(hi), _p(lo),
-                                          (stop_after + 1) if stop_after else (1 if per_phase_launches else 0),
+                                          (stop_after + 1) if stop_after else (1 if per_phase_launches else -int(group)),
                                           _lib.stream_of(images)), "sc_clip_tower_encode")
-    return (plan.n_phases if per_phase_launches else 1) + (0 if per_phase_launches else 1)
+    if per_phase_launches:
+        return plan.n_phases
+    pieces = 1 if group <= 0 else 1 + -(-(plan.n_phases - 3) // int(group))       # the three embedding phases, then `group` at a time
+    return 2 * pieces                                                              # a counter memset + a cooperative launch each

@@ -970,7 +970,7 @@ extern "C" int sc_clip_tower_plan(const ScClipConfig* cfg, const ScClipTowerWeig
 
 template <int SPLIT>
 static int launch_tower(const Phase* phases, const CUtensorMap* maps, int p0, int p1, unsigned* counter, const float* images,
-                        float* emb, float* raw, void* e_hi, void* e_lo, bool cooperative, cudaStream_t stream)
+                        float* emb, float* raw, void* e_hi, void* e_lo, bool cooperative, cudaStream_t stream, int group = 0)
 {
     cudaError_t e = cudaFuncSetAttribute(clip_tower_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) return (int)e;
@@ -980,11 +980,20 @@ static int launch_tower(const Phase* phases, const CUtensorMap* maps, int p0, in
     __nv_bfloat16* eh = reinterpret_cast<__nv_bfloat16*>(e_hi);
     __nv_bfloat16* el = reinterpret_cast<__nv_bfloat16*>(e_lo);
     if (cooperative) {
-        e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
-        if (e != cudaSuccess) return (int)e;
-        void* args[] = {(void*)&phases, (void*)&maps, (void*)&p0, (void*)&p1, (void*)&counter, (void*)&images, (void*)&emb, (void*)&raw, (void*)&eh, (void*)&el};
-        e = cudaLaunchCooperativeKernel((const void*)clip_tower_kernel<SPLIT>, dim3(sms), dim3(kThreads), args, kSmemBytes, stream);
-        return (int)e;
+        // group = 0: the whole tower in one launch. group = g > 0: one cooperative launch per g phases — pieces of ~0.1 ms that a
+        // stream of other kernels (the training step's render launches) can interleave with instead of one 1-3 ms block
+        const int step = group > 0 ? group : (p1 - p0);
+        for (int q0 = p0; q0 < p1; q0 += step) {
+            int q1 = q0 + step < p1 ? q0 + step : p1;
+            if (group > 0 && q0 == p0) q1 = (p0 + 3 < p1) ? p0 + 3 : p1;      // the embedding phases first, then `group` phases at a time
+            e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
+            if (e != cudaSuccess) return (int)e;
+            void* args[] = {(void*)&phases, (void*)&maps, (void*)&q0, (void*)&q1, (void*)&counter, (void*)&images, (void*)&emb, (void*)&raw, (void*)&eh, (void*)&el};
+            e = cudaLaunchCooperativeKernel((const void*)clip_tower_kernel<SPLIT>, dim3(sms), dim3(kThreads), args, kSmemBytes, stream);
+            if (e != cudaSuccess) return (int)e;
+            if (group > 0 && q0 == p0) q0 = q1 - step;
+        }
+        return 0;
     }
     for (int p = p0; p < p1; ++p) {                      // one ordinary launch per phase: the profiling / debugging form
         clip_tower_kernel<SPLIT><<<sms, kThreads, kSmemBytes, stream>>>(phases, maps, p, p + 1, counter, images, emb, raw, eh, el);
@@ -996,7 +1005,8 @@ static int launch_tower(const Phase* phases, const CUtensorMap* maps, int p0, in
 
 // images [B,3,S,S] fp32 (CLIP-normalised) -> emb [B,D] L2-normalised (+ optional unnormalised copy, + hi/lo bf16 planes).
 // mode 0: ONE cooperative launch for the whole tower; mode 1: one launch per phase (same device code; what ncu attributes
-// per GEMM); mode k >= 2: per-phase launches of the first k - 1 phases only (diagnostics). plan / workspace: as prepared by sc_clip_tower_plan for the same cfg and batch.
+// per GEMM); mode k >= 2: per-phase launches of the first k - 1 phases only (diagnostics); mode -g: cooperative launches of g phases
+// each (the three embedding phases first). plan / workspace: as prepared by sc_clip_tower_plan for the same cfg and batch.
 extern "C" int sc_clip_tower_encode(const ScClipConfig* cfg, const void* plan, int n_phases, void* workspace, const float* images,
                                     float* emb, float* emb_unnormalised, void* emb_hi, void* emb_lo, int mode, cudaStream_t stream)
 {
@@ -1006,6 +1016,7 @@ extern "C" int sc_clip_tower_encode(const ScClipConfig* cfg, const void* plan, i
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(reinterpret_cast<const uint8_t*>(plan) + align_up(n_phase_cap * sizeof(Phase), 128));
     unsigned* counter = reinterpret_cast<unsigned*>(workspace);
     if (mode >= 2) n_phases = (mode - 1 < n_phases) ? mode - 1 : n_phases;      // diagnostics: stop after the first (mode - 1) phases
-    if (cfg->split) return launch_tower<3>(phases, maps, 0, n_phases, counter, images, emb, emb_unnormalised, emb_hi, emb_lo, mode == 0, stream);
-    return launch_tower<1>(phases, maps, 0, n_phases, counter, images, emb, emb_unnormalised, emb_hi, emb_lo, mode == 0, stream);
+    const int group = mode < 0 ? -mode : 0;                                     // mode -g: cooperative launches of g phases each
+    if (cfg->split) return launch_tower<3>(phases, maps, 0, n_phases, counter, images, emb, emb_unnormalised, emb_hi, emb_lo, mode <= 0, stream, group);
+    return launch_tower<1>(phases, maps, 0, n_phases, counter, images, emb, emb_unnormalised, emb_hi, emb_lo, mode <= 0, stream, group);
 }
