@@ -84,7 +84,7 @@ __device__ __forceinline__ void ray_phase_backward(TT& T, const ScRenderArgs& a,
     #pragma unroll
                     for (int c = 0; c < 8; ++c) ub[c] = u8[c];
                 }
-                __syncthreads();
+                T.sync();
                 T.mark();
                 float delta = 0.f, E = 0.f, Tr = 0.f, ea = 0.f, w = 0.f, wp = 0.f, z = 0.f, fac = 0.f;
                 int rl = 0;
@@ -103,7 +103,7 @@ __device__ __forceinline__ void ray_phase_backward(TT& T, const ScRenderArgs& a,
                         for (int q = 0; q < 4; ++q) atomicAdd(&T.ray[RAYX_ACC + rl * 8 + q], v[q]);
                     }
                 }
-                __syncthreads();
+                T.sync();
                 T.mark();
                 if (tid < T.rays_per_tile) {
                     const int r = T.first + tid;
@@ -122,7 +122,7 @@ __device__ __forceinline__ void ray_phase_backward(TT& T, const ScRenderArgs& a,
                     T.ray[RAYX_NB + tid * 4 + 0] = nb[0]; T.ray[RAYX_NB + tid * 4 + 1] = nb[1]; T.ray[RAYX_NB + tid * 4 + 2] = nb[2];
                     if (r < a.n_per_image) a.depth_fac_bar[(size_t)T.b * a.n_per_image + r] = ub[4] * ac[0];
                 }
-                __syncthreads();
+                T.sync();
                 T.mark();
                 if (tid < M_TILE) {
                     const int p = tid, S = T.S, s = p % S;
@@ -173,7 +173,7 @@ __device__ __forceinline__ void ray_phase_backward(TT& T, const ScRenderArgs& a,
                     const float bb = warp_sum(sigma_bar * dsig_dbeta + c_bar * dc_dbeta);
                     if (lane == 0) atomicAdd(part_beta, bb);
                 }
-                __syncthreads();
+                T.sync();
                 T.mark();
 }
 

@@ -69,8 +69,11 @@ constexpr int SF_RAY = SF_PT + kPtVecsTc * M_TILE;                    // per-ray
 constexpr int SF_VACC = SF_RAY + 704;                                 // backward: vector-gradient accumulators (588 floats)
 constexpr int SF_MISC = SF_VACC + 592;                                // seq[64] bytes, seq_len, wg_mask
 constexpr int SF_END = SF_MISC + 32;
-constexpr int SMB_BAR = SMB_F32 + SF_END * 4;                         // mbarriers: wfull[4] wfree[4] mma_done, tmem slot
-constexpr int kSmemBytesTc = SMB_BAR + 128;                           // all-dynamic, __align__(1024): no static smem, no slack
+constexpr int SMB_BAR = SMB_F32 + SF_END * 4;                         // mbarriers: wfull[4] wfree[4] mma_done . tmem-slot ready[4] . ray_full[2] ray_free[2]
+constexpr int BAR_WFULL = 0, BAR_WFREE = 4, BAR_MMA_DONE = 8, BAR_TMEM_SLOT = 10, BAR_READY = 11, BAR_RAY_FULL = 16, BAR_RAY_FREE = 18;
+constexpr int SMB_CMD = SMB_BAR + 192;                                // role-split backward: command ring, 4 batches x 8 words
+constexpr int kCmdBatches = 4, kCmdWords = 8;
+constexpr int kSmemBytesTc = SMB_CMD + kCmdBatches * kCmdWords * 4;   // all-dynamic, __align__(1024): no static smem, no slack
 static_assert(kSmemBytesTc <= 232448, "exceeds the 227 KB shared memory of one CTA");
 enum PtVecTc : int { PX_A = scr::kPtVecs, PX_B = PX_A + 4, PX_C = PX_B + 4, PX_D = PX_C + 4 };   // 4 scratch vectors x [4 column groups]
 
@@ -173,7 +176,7 @@ constexpr uint32_t kDescHi = 0x40004040u;
 __device__ __forceinline__ uint32_t desc_lo_k128(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 __device__ __forceinline__ uint32_t desc_lo_mn128(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | ((1024u >> 4) << 16); }
 
-#ifdef SC_TC_NOINLINE_ISSUE          // the backward kernel (the forward kernel's loops keep its issue code cache-resident: inline is faster there)
+#if defined(SC_TC_NOINLINE_ISSUE) && !defined(SC_TC_ROLE_SPLIT)   // (was: the backward kernel before it got a dedicated issuing warp)
 #define SC_TC_ISSUE_FN static __device__ __noinline__
 #else
 #define SC_TC_ISSUE_FN __device__ __forceinline__
@@ -412,6 +415,16 @@ struct WeightRing {
         if (w0) scr::mbar_wait(wfull + (cur % NS), (cur / NS) & 1);
         n = cur + 1;
         return slots + (cur % NS) * kWSegBytes;
+    }
+    // role-split kernels: the dedicated issuing warp owns the ring; the operand hand-over is the command queue's business
+    __device__ __forceinline__ const uint8_t* wait_weights() {
+        const uint32_t cur = n;
+        scr::mbar_wait(wfull + (cur % NS), (cur / NS) & 1);
+        n = cur + 1;
+        return slots + (cur % NS) * kWSegBytes;
+    }
+    __device__ __forceinline__ void drain_issuer() {
+        for (uint32_t m = n; m < n + (uint32_t)NS - 1; ++m) scr::mbar_wait(wfull + (m % NS), (m / NS) & 1);
     }
     // issuing warp, AFTER issuing the MMAs that read the slot returned by the last acquire(): release that slot when they
     // complete, then prefetch matrix n + NS - 2 into the slot of the matrix before it (waiting for ITS MMAs, which are

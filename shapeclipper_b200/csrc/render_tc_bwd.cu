@@ -5,10 +5,16 @@
 // every weight-gradient GEMM is a UMMA 64x64x16 over the tile's 128 points (both operands = activation planes read
 // MN-major) that accumulates into one of 12 TMEM-resident matrices for the WHOLE kernel and is never waited for,
 // except before its operand buffers are overwritten. Vector gradients accumulate in shared memory. One flush at the end.
+//
+// Roles (640 threads): warps 0-15 = epilogue warps (TMEM lane quarter = warp & 3, column group = warp >> 2), warp 16 = MMA issuer
+// (interprets the command ring: weights, tcgen05.mma, commits, weight prefetch), warps 17-19 pad the issuer's warpgroup
+// (setmaxnreg works on warpgroups). With the issue code on warp 0 — also an epilogue warp — every phase waited for warp 0 to get
+// through 12-60 MMA issues (blocking on the tensor pipe's queue) AND its own epilogue before the next CTA barrier: clock64 trace,
+// 2-4 k cycles of a ~7 k-cycle phase. Now no epilogue warp ever waits for another one inside the sweeps.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define SC_TC_NOINLINE_ISSUE 1
+#define SC_TC_ROLE_SPLIT 1        // epilogue warps describe GEMMs as commands, a dedicated warp issues them (render_tc_tile.cuh)
 #include "render_ray.cuh"
 #include "render_tc_tile.cuh"
 
@@ -87,8 +93,51 @@ __device__ __forceinline__ void fold_pe_tc(const TileTC& T, const float (&v)[NC]
     }
 }
 
+constexpr int kBwdThreads = 640;         // 16 epilogue warps + the issuer's warpgroup
+constexpr int kIssuerWarp = 16;
+
+// The issuing warp (all 32 lanes; one elected lane executes the tcgen05 instructions): interprets the command batches.
+template <int PREC>
+__device__ __forceinline__ void issuer_loop(WeightRing& wr, const uint32_t* cmd, uint64_t* ready, uint64_t* mma_done, uint32_t tmem,
+                                            uint8_t* act0, uint32_t& wg_mask_out)
+{
+    uint32_t wg_init = 0;                 // which weight-gradient accumulators already hold data
+    wr.prologue();
+    for (uint32_t b = 0;; ++b) {
+        mbar_wait(ready + (b & 3u), (b >> 2) & 1u);
+        sctc::tc_fence_after();
+        const uint32_t* c = cmd + (b & 3u) * kCmdWords;
+        const uint32_t n = c[kCmdWords - 1];
+        bool end = false;
+#pragma unroll 1
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t w = uniform_u32(c[i]);
+            const uint32_t op = w & 3u, x = (w >> 2) & 15u;
+            const uint8_t* A = act0 + ((w >> 7) & 7u) * kActBytes;
+            if (op == TileTC::OP_GEMM) {
+                const uint8_t* ws = wr.wait_weights();
+                if (PREC == 1) issue_layer_gemm_single(tmem + 16u * x, A, ws, (w >> 6) & 1u);
+                else issue_layer_gemm(tmem + 16u * x, A, ws, (w >> 6) & 1u);
+                wr.release();
+            } else if (op == TileTC::OP_WGRAD) {
+                const uint8_t* R = act0 + ((w >> 10) & 7u) * kActBytes;
+                if (PREC == 1) issue_wgrad_single(wg_taddr(tmem, (int)x), A, R, (wg_init >> x) & 1u);
+                else issue_wgrad(wg_taddr(tmem, (int)x), A, R, (wg_init >> x) & 1u);
+                wg_init |= 1u << x;
+            } else if (op == TileTC::OP_COMMIT) {
+                umma_commit_elect(mma_done);
+            } else {
+                end = true;
+            }
+        }
+        if (end) break;
+    }
+    wr.drain_issuer();
+    wg_mask_out = wg_init;
+}
+
 template <int MODE, int PREC>      // PREC = ScRenderArgs::precision, compile-time (see render_tc.cu)
-__global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRenderArgs a, float* stash_base)
+__global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScRenderArgs a, float* stash_base)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     int8_t* seq = reinterpret_cast<int8_t*>(reinterpret_cast<float*>(smem + SMB_F32) + SF_MISC);
@@ -97,15 +146,17 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
     uint32_t& wg_mask = *reinterpret_cast<uint32_t*>(reinterpret_cast<float*>(smem + SMB_F32) + SF_MISC + 17);
     const uint8_t* blob = reinterpret_cast<const uint8_t*>(a.blob);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMB_BAR);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_TMEM_SLOT);
+    uint32_t* cmd = reinterpret_cast<uint32_t*>(smem + SMB_CMD);
 
     const bool second = (MODE == 0) || (a.want_grad && a.grad_bar != nullptr);
     const bool use_saved = (MODE == 0) && a.saved != nullptr;      // activations saved by sc_render_tc_forward: no recompute
     float* part = a.grad_partial + (size_t)blockIdx.x * kGradFloats;
-    for (int i = threadIdx.x; i < kGradFloats; i += kThreads) part[i] = 0.f;
-    for (int i = threadIdx.x; i < VA_FLOATS; i += kThreads) vacc[i] = 0.f;
+    for (int i = threadIdx.x; i < kGradFloats; i += kBwdThreads) part[i] = 0.f;
+    for (int i = threadIdx.x; i < VA_FLOATS; i += kBwdThreads) vacc[i] = 0.f;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 9; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < kCmdBatches; ++i) mbar_init(bars + BAR_READY + i, 16);
         mbar_fence_init();
         int len; build_seq_tc_bwd(seq, len, MODE, second, !use_saved); seq_len = len;
     }
@@ -113,8 +164,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
     {
         float* f = reinterpret_cast<float*>(smem + SMB_F32);
         const float* src = reinterpret_cast<const float*>(blob + kTcConstOffsetBytes);
-        for (int i = threadIdx.x; i < kConstFloats; i += kThreads) f[SF_CONST + i] = src[i];
-        for (int i = threadIdx.x; i < 64; i += kThreads) {
+        for (int i = threadIdx.x; i < kConstFloats; i += kBwdThreads) f[SF_CONST + i] = src[i];
+        for (int i = threadIdx.x; i < 64; i += kBwdThreads) {
             f[SF_BIAS + 3 * 64 + i] = src[C_B3 + i]; f[SF_BIAS + 4 * 64 + i] = src[C_B4 + i];
             f[SF_BIAS + 6 * 64 + i] = src[C_C1R + i]; f[SF_BIAS + 7 * 64 + i] = src[C_C2R + i];
         }
@@ -123,17 +174,41 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
     __syncthreads();
     sctc::tc_fence_after();
 
+    const int per_tile_ = (MODE == 0) ? M_TILE / a.n_samples : M_TILE;
+    const int total_ = a.batch * ((a.n_per_image + per_tile_ - 1) / per_tile_);
+    const bool active = (int)blockIdx.x < total_;
+    const uint32_t tmem_base = *tmem_slot;
+    const int warp_id = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform for the compiler too
+
+    if (warp_id >= kIssuerWarp) {
+        // ---------------------------------------------------------------------------------------- the issuer's warpgroup
+        // register budget: 640 x 96 at launch; setmaxnreg.inc can only take what a .dec has RELEASED into the CTA's pool (the SM's
+        // unallocated registers are not part of it: asking for more than was released blocks forever): 128 x 32 released here =
+        // 512 x 8 taken by the epilogue warps
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (warp_id == kIssuerWarp && active) {
+            WeightRing wr;
+            wr.blob = blob; wr.slots = smem + SMB_W_BWD; wr.wfull = bars + BAR_WFULL; wr.wfree = bars + BAR_WFREE;
+            wr.seq = seq; wr.seq_len = seq_len; wr.NS = 2; wr.w0 = true;
+            uint32_t mask = 0;
+            issuer_loop<PREC>(wr, cmd, bars + BAR_READY, bars + BAR_MMA_DONE, tmem_base, smem + SMB_ACT, mask);
+            if ((threadIdx.x & 31) == 0) wg_mask = mask;
+        }
+        __syncthreads();                  // (A) the issuer is done: wg_mask is published
+        __syncthreads();                  // (B) the epilogue warps have flushed TMEM
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+
     TileTC T;
     {   // same carve-up as the forward kernel, but 5 operand buffers + 2 weight slots
         for (int i = 0; i < kNumAct; ++i) T.act[i] = smem + SMB_ACT + i * kActBytes;
         float* f = reinterpret_cast<float*>(smem + SMB_F32);
         T.cst = f + SF_CONST; T.cb = f + SF_CB; T.pt = f + SF_PT; T.ray = f + SF_RAY; T.bias = f + SF_BIAS;
-        T.wr.blob = blob; T.wr.slots = smem + SMB_W_BWD; T.wr.wfull = bars; T.wr.wfree = bars + 4;
-        T.wr.seq = seq; T.wr.seq_len = seq_len; T.wr.NS = 2;
-        T.mma_done = bars + 8; T.mma_phase = 0;
+        T.cmd = cmd; T.ready = bars + BAR_READY; T.batch = 0; T.ncmd = 0;
+        T.mma_done = bars + BAR_MMA_DONE; T.mma_phase = 0;
         T.tid = threadIdx.x; T.lane = threadIdx.x & 31; T.warp = threadIdx.x >> 5;
-        T.w0 = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0) == 0;      // the issuing warp, warp-uniform for the compiler too
-        T.wr.w0 = T.w0;
+        T.w0 = false;
         T.wide = false;            // TMEM is full here (12 weight-gradient accumulators)
         T.single = (PREC == 1);
         T.row = 32 * (T.warp & 3) + T.lane; T.ch = T.warp >> 2;
@@ -141,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
         T.trace = (MODE == 0) ? reinterpret_cast<long long*>(a.points_bar) : nullptr; T.trace_n = 0;
 #endif
     }
-    T.tmem = *tmem_slot;
+    T.tmem = tmem_base;
     T.stash = stash_base + (size_t)blockIdx.x * TS_PLANES_BWD * kStashPlane;
     T.S = (MODE == 0) ? a.n_samples : 1;
     T.rays_per_tile = (MODE == 0) ? M_TILE / a.n_samples : M_TILE;
@@ -149,20 +224,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
     const int tid = T.tid, lane = T.lane, r = T.row, ch = T.ch, c0 = NC * T.ch;
     float* const sc = T.stash;            // per-CTA scratch planes (FB, SB: written and re-read inside one tile)
     float* st = T.stash;                  // activation planes: the same scratch (recompute) or the tile's saved block
-    const bool w0 = T.w0;
-    uint32_t wg_init = 0;                 // issuing warp: which weight-gradient accumulators already hold data
-    auto wgrad = [&](int m, const uint8_t* L, const uint8_t* R) {      // issuing warp only (all 32 lanes)
-        if (PREC == 1) issue_wgrad_single(wg_taddr(T.tmem, m), L, R, (wg_init >> m) & 1u);
-        else issue_wgrad(wg_taddr(T.tmem, m), L, R, (wg_init >> m) & 1u);
-        wg_init |= 1u << m;
-    };
-    // all threads: make the operand stores visible to the tensor core and line the CTA up (no weights involved)
-    auto publish = [&]() { sctc::fence_proxy_async(); sctc::tc_fence_before(); __syncthreads(); sctc::tc_fence_after(); };
+    auto wgrad = [&](int m, const uint8_t* L, const uint8_t* R) { T.wgrad(m, L, R); };
     // wait until every MMA issued so far (layer GEMMs and weight gradients) has completed
-    auto drain_mma = [&]() {
-        T.commit();
-        mbar_wait(T.mma_done, T.mma_phase); T.mma_phase ^= 1; sctc::tc_fence_after();
-    };
+    auto drain_mma = [&]() { T.commit(); T.wait_mma(); };
 
     const int per_tile = (MODE == 0) ? T.rays_per_tile : M_TILE;
     const int tiles_per_image = (a.n_per_image + per_tile - 1) / per_tile;
@@ -170,13 +234,12 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
     const int cb_rows = a.detach_latent ? CB_C0D : CB_C0;
     float v[NC], h[NC], w1[NC], w2[NC];
 
-    if ((int)blockIdx.x < total) {
-        T.wr.prologue();
+    if (active) {
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
             T.b = tile / tiles_per_image;
             T.first = (tile % tiles_per_image) * per_tile;
             float* cbb = a.cb_bar + (size_t)T.b * kCbRows * 64;
-            __syncthreads();
+            T.sync();
             T.mark();                                                            // [trace] tile start
             tc_tile_setup<MODE>(T, a);
             T.mark();                                                            // [trace] setup done
@@ -184,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 st = reinterpret_cast<float*>(a.saved) + (size_t)tile * TS_SAVED_PLANES * kStashPlane;
                 if (MODE == 0) st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);      // r2, consumed after the ray phase: HBM latency hidden
                 saved_vectors<false>(T, st + TS_SAVED_PV * kStashPlane);
-                __syncthreads();
+                T.sync();
                 T.mark();                                                        // [trace] saved vectors loaded
             } else {
                 tc_tile_forward<MODE, true>(T, a, second, MODE == 0);
@@ -201,9 +264,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
 #pragma unroll
                     for (int c = 0; c < 3; ++c) T.pv(PV_GXB0 + c)[tid] = (valid && second) ? a.grad_bar[g * 3 + c] : 0.f;
                 }
-                __syncthreads();
+                T.sync();
             } else {
-                ray_phase_backward(T, a, vacc + VA_BETA, kThreads);
+                ray_phase_backward(T, a, vacc + VA_BETA, 512);
                 T.mark();                                                        // [trace] ray phase done
 
                 // ============================================================================ RGB backward
@@ -217,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                         if (lane == 0) atomicAdd(vacc + VA_C3R + c, sres);
                     }
                 }
-                __syncthreads();
+                T.sync();
                 T.mark();                                                        // [trace] o3_bar done
                 // o2_bar = (V3^T o3_bar) * [r2 > 0] -> Y ; dV3 += o3_bar (x) r2
                 if (!use_saved) st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);
@@ -238,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 plane_to_act(T, st + (TS_R + 1) * kStashPlane, T.Z(), h);      // r1 -> Z (h keeps this thread's r1 values)
                 T.gemm(TM_ACC0, T.Y(), false);                                   // V2T : r1_bar = V2^T o2_bar
                 T.commit();                                                      // the epilogue overlaps the weight-gradient MMAs
-                if (w0) wgrad(WG_V2, T.Y(), T.Z());
+                wgrad(WG_V2, T.Y(), T.Z());
                 T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) v[i] = h[i] > 0.f ? v[i] : 0.f;
@@ -247,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 plane_to_act(T, st + (TS_R + 0) * kStashPlane, T.U(), h);      // r0 -> U
                 T.gemm(TM_ACC0, T.X(), false);                                   // V1T
                 T.commit();
-                if (w0) wgrad(WG_V1, T.X(), T.U());
+                wgrad(WG_V1, T.X(), T.U());
                 T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) v[i] = h[i] > 0.f ? v[i] : 0.f;
@@ -257,13 +320,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 T.gemm(TM_ACC0, T.Z(), false);                                   // V0FT -> feat_bar
                 T.gemm(TM_ACC1, T.Z(), false);                                   // V0PT -> pe_bar (rgb)
                 T.commit();
-                if (w0) { wgrad(WG_V0F, T.Z(), T.Y()); wgrad(WG_V0P, T.Z(), T.P()); }
+                wgrad(WG_V0F, T.Z(), T.Y()); wgrad(WG_V0P, T.Z(), T.P());
                 T.wait_and_load(TM_ACC0, v);
                 st_store(sc + TS_FB * kStashPlane, r, ch, v);
                 colsum_shared(vacc + VA_B5F, v, ch, lane);
                 tmem_ld_32x16(T.tmem + TM_ACC1 + ((uint32_t)(32 * (T.warp & 3)) << 16) + (uint32_t)c0, v);
                 fold_pe_tc(T, v);
-                __syncthreads();
+                T.sync();
             }
 
             // ================================================================================ second-order sweep
@@ -304,13 +367,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                     }
                     st_store(sc + (TS_SB + l) * kStashPlane, r, ch, w2);
                     row_store(qcur, r, ch, v); row_store(T.Z(), r, ch, h);
-                    publish();
-                    if (w0) {
-                        if (l < 3) wgrad(l == 0 ? WG_A0 : (l == 1 ? WG_A1 : WG_A2), T.Z(), T.X());
-                        if (l == 1) wgrad(WG_B1, T.Z(), qprev);
-                        if (l == 2) wgrad(WG_B2, T.Z(), qprev);
-                        if (l == 3) wgrad(WG_W3, T.Z(), qprev);
-                    }
+                    // (queued; submitted together with the next phase's layer GEMM)
+                    if (l < 3) wgrad(l == 0 ? WG_A0 : (l == 1 ? WG_A1 : WG_A2), T.Z(), T.X());
+                    if (l == 1) wgrad(WG_B1, T.Z(), qprev);
+                    if (l == 2) wgrad(WG_B2, T.Z(), qprev);
+                    if (l == 3) wgrad(WG_W3, T.Z(), qprev);
                     // Z (g_l) and qprev are re-written in the next iteration's epilogue, i.e. after its finish_and_load,
                     // whose commit covers these weight-gradient MMAs.
                 }
@@ -329,8 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 st_store(sc + (TS_SB + 4) * kStashPlane, r, ch, w2);
                 colsum_shared(vacc + VA_W5, w1, ch, lane);
                 row_store(T.Z(), r, ch, h);
-                publish();
-                if (w0) wgrad(WG_W4, T.Z(), T.U());
+                wgrad(WG_W4, T.Z(), T.U());
             }
 
             // ================================================================================ first-order sweep
@@ -365,8 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
             colsum_shared(vacc + VA_W5, w1, ch, lane);
             if (MODE == 0) {
                 row_store(T.Z(), r, ch, h);                                      // h4 -> Z  (Z = g4: weight gradient W4 retired above)
-                publish();
-                if (w0) wgrad(WG_W5F, T.X(), T.Z());
+                wgrad(WG_W5F, T.X(), T.Z());
             }
             // layers 3..0: dW_{l+1} += a_{l+1}_bar (x) h_l ; a_l_bar = (W_{l+1}^T a_{l+1}_bar) s_l + SB_l t_l
             //   a_bar alternates Y -> X -> Y -> X -> Y ; h_l is loaded into U / Z alternately
@@ -379,10 +438,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 if (l < 2) { T.gemm(TM_ACC1, acur, false); }                     // A2T | A1T  -> pe_bar
                 T.gemm(TM_ACC0, acur, false);                                    // W4T | W3T | B2T | B1T
                 T.commit();
-                if (w0) {
-                    wgrad(l == 3 ? WG_W4 : (l == 2 ? WG_W3 : (l == 1 ? WG_B2 : WG_B1)), acur, hbuf);
-                    if (l < 2) wgrad(l == 1 ? WG_A2 : WG_A1, acur, T.P());
-                }
+                wgrad(l == 3 ? WG_W4 : (l == 2 ? WG_W3 : (l == 1 ? WG_B2 : WG_B1)), acur, hbuf);
+                if (l < 2) wgrad(l == 1 ? WG_A2 : WG_A1, acur, T.P());
                 if (second) st_load(sc + (TS_SB + l) * kStashPlane, r, ch, w2);
                 T.wait_and_load(TM_ACC0, v);
 #pragma unroll
@@ -401,10 +458,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
             }
             // a0_bar is in Y: dA0 += a0_bar (x) pe ; pe_bar += A0^T a0_bar
             T.gemm(TM_ACC1, T.Y(), false);                                       // A0T
-            if (w0) wgrad(WG_A0, T.Y(), T.P());
+            wgrad(WG_A0, T.Y(), T.P());
             T.finish_and_load(TM_ACC1, w1);
             fold_pe_tc(T, w1);
-            __syncthreads();
+            T.sync();
             T.mark();                                                            // [trace] sweeps done
 
             // ================================================================================ x_bar -> outputs
@@ -444,10 +501,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 }
             }
         }
-        T.wr.drain();
-        drain_mma();
-        if (tid == 0) wg_mask = wg_init;
-        __syncthreads();
+        T.commit(); T.end();                 // retire every MMA, then let the issuer drain its weight ring and publish wg_mask
+        T.wait_mma();
+    }
+    __syncthreads();                         // (A) all 640 threads
+    if (active) {
         // ---- flush: 12 TMEM-resident weight gradients + the shared vector accumulators -> this CTA's partial
         const int goff[NWG] = {G_A0, G_A1, G_A2, G_B1, G_B2, G_W3, G_W4, G_W5F, G_V0P, G_V0F, G_V1, G_V2};
 #pragma unroll 1
@@ -465,11 +523,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_tc_bwd_kernel(const ScRend
                 }
             }
         }
-        __syncthreads();
-        for (int i = tid; i < VA_FLOATS; i += kThreads) part[G_V3 + i] = vacc[i];
+        T.sync();
+        for (int i = tid; i < VA_FLOATS; i += 512) part[G_V3 + i] = vacc[i];
     }
     sctc::tc_fence_before();
-    __syncthreads();
+    __syncthreads();                         // (B)
     if ((threadIdx.x >> 5) == 0) sctc::tmem_dealloc<512>(T.tmem);
 }
 
@@ -493,7 +551,7 @@ extern "C" int sc_render_tc_backward(const ScRenderArgs* a, cudaStream_t stream)
 #define SC_LAUNCH_BWD(MODE_, PREC_) do { \
         err = cudaFuncSetAttribute(render_tc_bwd_kernel<MODE_, PREC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc); \
         if (err != cudaSuccess) return (int)err; \
-        render_tc_bwd_kernel<MODE_, PREC_><<<sms, sct::kThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch); } while (0)
+        render_tc_bwd_kernel<MODE_, PREC_><<<sms, sct::kBwdThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch); } while (0)
     const bool single = a->precision == 1;
     if (a->mode == 0) { if (single) SC_LAUNCH_BWD(0, 1); else SC_LAUNCH_BWD(0, 0); }
     else { if (single) SC_LAUNCH_BWD(1, 1); else SC_LAUNCH_BWD(1, 0); }

@@ -33,29 +33,11 @@ struct TileTC {
     __device__ __forceinline__ uint8_t* Z() const { return act[3]; }
     __device__ __forceinline__ uint8_t* U() const { return act[4]; }
 
+#ifndef SC_TC_ROLE_SPLIT
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
     // thread 0: commit the phase's layer GEMMs. MMAs issued AFTER this (weight gradients) are covered by the NEXT phase's
     // commit: their operand buffers must stay untouched until the next wait_and_load() has returned.
     __device__ __forceinline__ void commit() { if (w0) umma_commit_elect(mma_done); }
-    __device__ __forceinline__ void finish_and_load(uint32_t acc_col, float (&v)[NC]) { commit(); wait_and_load(acc_col, v); }
-    // everyone: wait for the accumulator, then read this thread's NC columns
-    __device__ __forceinline__ void wait_and_load(uint32_t acc_col, float (&v)[NC]) {
-        mark();
-        scr::mbar_wait(mma_done, mma_phase);
-        mark();
-        mma_phase ^= 1;
-        sctc::tc_fence_after();
-        if (wide) {
-            float u[NC];
-            const uint32_t base = tmem + 2 * acc_col + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(NC * ch);
-            tmem_ld_32x16(base, v);
-            tmem_ld_32x16(base + 64, u);
-#pragma unroll
-            for (int i = 0; i < NC; ++i) v[i] += u[i];
-        } else {
-            tmem_ld_32x16(tmem + acc_col + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(NC * ch), v);
-        }
-        mark();
-    }
     // one layer GEMM: acquire weights, (thread 0) issue + release
     __device__ __forceinline__ void gemm(uint32_t acc_col, const uint8_t* a, bool accumulate) {
         mark();
@@ -67,6 +49,65 @@ struct TileTC {
             else issue_layer_gemm(tmem + acc_col, a, w, accumulate);
             wr.release();
         }
+    }
+    __device__ __forceinline__ void submit() {}
+#else
+    // ---- role-split kernels (render_tc_bwd.cu): the 16 epilogue warps never issue an MMA. They describe the work as COMMANDS
+    // (thread 0 writes them into a 4-batch ring in shared memory), publish their operand stores (fence.proxy.async, one
+    // mbarrier arrive per warp on ready[batch & 3] — no CTA barrier, nobody waits for the slowest warp) and go on to wait for the
+    // accumulator; a dedicated warp (warp 16) interprets the commands: waits for the weights, issues, commits, prefetches.
+    // Command word: bits 0-1 op, 2-5 accumulator column / 16 (GEMM) or weight-gradient matrix (WGRAD), 6 accumulate,
+    // 7-9 operand buffer A (act[] index), 10-12 operand buffer B (WGRAD). Word 7 of a batch = its length.
+    // At most ONE batch without a COMMIT may be submitted between two batches with one (the epilogue warps wait for every
+    // commit), so the epilogue warps are never more than two batches ahead of the issuer: the ring of four cannot wrap.
+    uint32_t* cmd;              // [kCmdBatches][kCmdWords]
+    uint64_t* ready;            // [kCmdBatches], count 16 (one arrive per epilogue warp)
+    uint32_t batch, ncmd;       // uniform over the epilogue warps
+    enum : uint32_t { OP_GEMM = 0, OP_COMMIT = 1, OP_WGRAD = 2, OP_END = 3 };
+    __device__ __forceinline__ void sync() const { asm volatile("bar.sync 2, 512;" ::: "memory"); }
+    __device__ __forceinline__ uint32_t buf_index(const uint8_t* a) const { return (uint32_t)(a - act[0]) / (uint32_t)kActBytes; }
+    __device__ __forceinline__ void push(uint32_t c) { if (tid == 0) cmd[(batch & 3u) * kCmdWords + ncmd] = c; ++ncmd; }
+    __device__ __forceinline__ void gemm(uint32_t acc_col, const uint8_t* a, bool accumulate) {
+        push(OP_GEMM | ((acc_col >> 4) << 2) | ((accumulate ? 1u : 0u) << 6) | (buf_index(a) << 7));
+    }
+    __device__ __forceinline__ void commit() { push(OP_COMMIT); }
+    __device__ __forceinline__ void wgrad(int m, const uint8_t* L, const uint8_t* R) {
+        push(OP_WGRAD | ((uint32_t)m << 2) | (buf_index(L) << 7) | (buf_index(R) << 10));
+    }
+    __device__ __forceinline__ void end() { push(OP_END); }
+    __device__ __forceinline__ void submit() {
+        if (ncmd == 0) return;
+        if (tid == 0) cmd[(batch & 3u) * kCmdWords + (kCmdWords - 1)] = ncmd;
+        sctc::fence_proxy_async();                 // this thread's operand stores -> visible to the tensor core's (async-proxy) reads
+        sctc::tc_fence_before();                   // its tcgen05.ld of the accumulator the next MMA may overwrite
+        __syncwarp();
+        if (lane == 0) sctc::mbar_arrive(ready + (batch & 3u));
+        ++batch; ncmd = 0;
+    }
+#endif
+    __device__ __forceinline__ void finish_and_load(uint32_t acc_col, float (&v)[NC]) { commit(); wait_and_load(acc_col, v); }
+    // everyone: wait for the accumulator, then read this thread's NC columns
+    __device__ __forceinline__ void wait_mma() {
+        submit();
+        mark();
+        scr::mbar_wait(mma_done, mma_phase);
+        mark();
+        mma_phase ^= 1;
+        sctc::tc_fence_after();
+    }
+    __device__ __forceinline__ void wait_and_load(uint32_t acc_col, float (&v)[NC]) {
+        wait_mma();
+        if (wide) {
+            float u[NC];
+            const uint32_t base = tmem + 2 * acc_col + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(NC * ch);
+            tmem_ld_32x16(base, v);
+            tmem_ld_32x16(base + 64, u);
+#pragma unroll
+            for (int i = 0; i < NC; ++i) v[i] += u[i];
+        } else {
+            tmem_ld_32x16(tmem + acc_col + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(NC * ch), v);
+        }
+        mark();
     }
 };
 
@@ -216,7 +257,7 @@ template <int MODE>
 __device__ __forceinline__ void tc_tile_setup(const TileTC& T, const ScRenderArgs& a)
 {
     for (int i = T.tid; i < 256; i += kThreads) T.cb[i] = a.cb[(size_t)T.b * 256 + i];
-    __syncthreads();
+    T.sync();
     // every thread (row p, column group ch) derives the sample point of its row; group 0 publishes the per-point vectors
     const int p = T.row;
     float x0, x1, x2, z = 0.f;
@@ -351,7 +392,7 @@ __device__ __forceinline__ void tc_tile_forward(TileTC& T, const ScRenderArgs& a
             if (STASH_ALL) st_store(st + (TS_R + l) * kStashPlane, r, ch, v);
         }
     }
-    __syncthreads();
+    T.sync();
     if (T.tid < M_TILE) {
         const int p = T.tid;
         auto sum4 = [&](int base) { return T.pv(base)[p] + T.pv(base + 1)[p] + T.pv(base + 2)[p] + T.pv(base + 3)[p]; };
@@ -362,7 +403,7 @@ __device__ __forceinline__ void tc_tile_forward(TileTC& T, const ScRenderArgs& a
             T.pv(PV_COL2)[p] = 1.f / (1.f + expf(-(T.cst[C_C3R + 2] + sum4(PX_D))));
         }
     }
-    if (MODE == 1 && !want_grad) { __syncthreads(); return; }
+    if (MODE == 1 && !want_grad) { T.sync(); return; }
 
     // ---- gradient pass. Stash reads are issued BEFORE waiting for the MMA so that their L2 latency overlaps it.
     st_load(st + (TS_H + 4) * kStashPlane, r, ch, h);
@@ -390,7 +431,7 @@ __device__ __forceinline__ void tc_tile_forward(TileTC& T, const ScRenderArgs& a
         pe_fold(T.P(), r, ch, v, g);
         T.pv(PX_A + ch)[r] = g[0]; T.pv(PX_B + ch)[r] = g[1]; T.pv(PX_C + ch)[r] = g[2];
     }
-    __syncthreads();
+    T.sync();
     if (T.tid < M_TILE) {
         const int p = T.tid;
         auto sum4 = [&](int base) { return T.pv(base)[p] + T.pv(base + 1)[p] + T.pv(base + 2)[p] + T.pv(base + 3)[p]; };
@@ -406,7 +447,7 @@ __device__ __forceinline__ void tc_tile_forward(TileTC& T, const ScRenderArgs& a
             T.pv(PV_NS0)[p] = u0 * inv; T.pv(PV_NS1)[p] = u1 * inv; T.pv(PV_NS2)[p] = u2 * inv;
         }
     }
-    __syncthreads();
+    T.sync();
 }
 
 }  // namespace sct
