@@ -98,13 +98,13 @@ constexpr int kIssuerWarp = 16;
 
 // The issuing warp (all 32 lanes; one elected lane executes the tcgen05 instructions): interprets the command batches.
 template <int PREC>
-__device__ __forceinline__ void issuer_loop(WeightRing& wr, const uint32_t* cmd, uint64_t* ready, uint64_t* mma_done, uint32_t tmem,
+__device__ __forceinline__ void issuer_loop(WeightRing& wr, const uint32_t* cmd, uint64_t* mma_done, uint32_t tmem,
                                             uint8_t* act0, uint32_t& wg_mask_out)
 {
     uint32_t wg_init = 0;                 // which weight-gradient accumulators already hold data
     wr.prologue();
     for (uint32_t b = 0;; ++b) {
-        mbar_wait(ready + (b & 3u), (b >> 2) & 1u);
+        if (b & 1u) asm volatile("bar.sync 5, 544;" ::: "memory"); else asm volatile("bar.sync 4, 544;" ::: "memory");
         sctc::tc_fence_after();
         const uint32_t* c = cmd + (b & 3u) * kCmdWords;
         const uint32_t n = c[kCmdWords - 1];
@@ -156,7 +156,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
     for (int i = threadIdx.x; i < VA_FLOATS; i += kBwdThreads) vacc[i] = 0.f;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 9; ++i) mbar_init(bars + i, 1);
-        for (int i = 0; i < kCmdBatches; ++i) mbar_init(bars + BAR_READY + i, 16);
         mbar_fence_init();
         int len; build_seq_tc_bwd(seq, len, MODE, second, !use_saved); seq_len = len;
     }
@@ -191,7 +190,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
             wr.blob = blob; wr.slots = smem + SMB_W_BWD; wr.wfull = bars + BAR_WFULL; wr.wfree = bars + BAR_WFREE;
             wr.seq = seq; wr.seq_len = seq_len; wr.NS = 2; wr.w0 = true;
             uint32_t mask = 0;
-            issuer_loop<PREC>(wr, cmd, bars + BAR_READY, bars + BAR_MMA_DONE, tmem_base, smem + SMB_ACT, mask);
+            issuer_loop<PREC>(wr, cmd, bars + BAR_MMA_DONE, tmem_base, smem + SMB_ACT, mask);
             if ((threadIdx.x & 31) == 0) wg_mask = mask;
         }
         __syncthreads();                  // (A) the issuer is done: wg_mask is published
@@ -205,7 +204,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
         for (int i = 0; i < kNumAct; ++i) T.act[i] = smem + SMB_ACT + i * kActBytes;
         float* f = reinterpret_cast<float*>(smem + SMB_F32);
         T.cst = f + SF_CONST; T.cb = f + SF_CB; T.pt = f + SF_PT; T.ray = f + SF_RAY; T.bias = f + SF_BIAS;
-        T.cmd = cmd; T.ready = bars + BAR_READY; T.batch = 0; T.ncmd = 0;
+        T.cmd = cmd; T.batch = 0; T.ncmd = 0;
         T.mma_done = bars + BAR_MMA_DONE; T.mma_phase = 0;
         T.tid = threadIdx.x; T.lane = threadIdx.x & 31; T.warp = threadIdx.x >> 5;
         T.w0 = false;
@@ -245,7 +244,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
             T.mark();                                                            // [trace] setup done
             if (use_saved) {
                 st = reinterpret_cast<float*>(a.saved) + (size_t)tile * TS_SAVED_PLANES * kStashPlane;
-                if (MODE == 0) st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);      // r2, consumed after the ray phase: HBM latency hidden
+                if (MODE == 0) {                                                 // r2, r1: consumed after the ray phase, HBM latency hidden
+                    st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);
+                    st_load(st + (TS_R + 1) * kStashPlane, r, ch, w1);
+                }
                 saved_vectors<false>(T, st + TS_SAVED_PV * kStashPlane);
                 T.sync();
                 T.mark();                                                        // [trace] saved vectors loaded
@@ -283,7 +285,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
                 T.sync();
                 T.mark();                                                        // [trace] o3_bar done
                 // o2_bar = (V3^T o3_bar) * [r2 > 0] -> Y ; dV3 += o3_bar (x) r2
-                if (!use_saved) st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);
+                // Every activation plane is loaded ONE PHASE AHEAD of its use (into w1, between the submit and the wait of the phase
+                // before): a load issued right where the plane is needed costs a full L2/HBM round trip per phase, and nothing hides
+                // it — all 16 warps run the same phase.
+                if (!use_saved) { st_load(st + (TS_R + 2) * kStashPlane, r, ch, h); st_load(st + (TS_R + 1) * kStashPlane, r, ch, w1); }
                 {
                     const float o0 = T.pv(PV_CB0)[r], o1 = T.pv(PV_CB1)[r], o2 = T.pv(PV_CB2)[r];
 #pragma unroll
@@ -291,36 +296,52 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
                         const int k = c0 + i;
                         const float t = T.cst[C_V3 + k] * o0 + T.cst[C_V3 + 64 + k] * o1 + T.cst[C_V3 + 128 + k] * o2;
                         v[i] = h[i] > 0.f ? t : 0.f;
-                        w1[i] = o0 * h[i]; w2[i] = o1 * h[i]; h[i] = o2 * h[i];
                     }
-                    colsum_shared(vacc + VA_V3, w1, ch, lane); colsum_shared(vacc + VA_V3 + 64, w2, ch, lane);
-                    colsum_shared(vacc + VA_V3 + 128, h, ch, lane);
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) w2[i] = o0 * h[i];
+                    colsum_shared(vacc + VA_V3, w2, ch, lane);
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) w2[i] = o1 * h[i];
+                    colsum_shared(vacc + VA_V3 + 64, w2, ch, lane);
+#pragma unroll
+                    for (int i = 0; i < NC; ++i) w2[i] = o2 * h[i];
+                    colsum_shared(vacc + VA_V3 + 128, w2, ch, lane);
                 }
                 row_store(T.Y(), r, ch, v);
                 colsum_shared(vacc + VA_C2R, v, ch, lane);
-                plane_to_act(T, st + (TS_R + 1) * kStashPlane, T.Z(), h);      // r1 -> Z (h keeps this thread's r1 values)
+#pragma unroll
+                for (int i = 0; i < NC; ++i) h[i] = w1[i];
+                row_store(T.Z(), r, ch, h);                                      // r1 -> Z (h keeps this thread's r1 values)
                 T.gemm(TM_ACC0, T.Y(), false);                                   // V2T : r1_bar = V2^T o2_bar
                 T.commit();                                                      // the epilogue overlaps the weight-gradient MMAs
                 wgrad(WG_V2, T.Y(), T.Z());
+                T.submit();
+                st_load(st + (TS_R + 0) * kStashPlane, r, ch, w1);              // r0, one phase ahead
                 T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) v[i] = h[i] > 0.f ? v[i] : 0.f;
                 row_store(T.X(), r, ch, v);                                      // o1_bar -> X
                 colsum_shared(vacc + VA_C1R, v, ch, lane);
-                plane_to_act(T, st + (TS_R + 0) * kStashPlane, T.U(), h);      // r0 -> U
+#pragma unroll
+                for (int i = 0; i < NC; ++i) h[i] = w1[i];
+                row_store(T.U(), r, ch, h);                                      // r0 -> U
                 T.gemm(TM_ACC0, T.X(), false);                                   // V1T
                 T.commit();
                 wgrad(WG_V1, T.X(), T.U());
+                T.submit();
+                st_load(st + TS_FEAT * kStashPlane, r, ch, w1);                 // feat, one phase ahead
                 T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) v[i] = h[i] > 0.f ? v[i] : 0.f;
                 row_store(T.Z(), r, ch, v);                                      // o0_bar -> Z  (Z: wgrad V2 completed with the V1T phase)
                 colsum_global(cbb + CB_RGB * 64, v, ch, lane);
-                plane_to_act(T, st + TS_FEAT * kStashPlane, T.Y(), h);         // feat -> Y
+                row_store(T.Y(), r, ch, w1);                                     // feat -> Y
                 T.gemm(TM_ACC0, T.Z(), false);                                   // V0FT -> feat_bar
                 T.gemm(TM_ACC1, T.Z(), false);                                   // V0PT -> pe_bar (rgb)
                 T.commit();
                 wgrad(WG_V0F, T.Z(), T.Y()); wgrad(WG_V0P, T.Z(), T.P());
+                T.submit();
+                if (second) st_load(st + TS_GPE * kStashPlane, r, ch, h);       // gpe, for the second-order prologue
                 T.wait_and_load(TM_ACC0, v);
                 st_store(sc + TS_FB * kStashPlane, r, ch, v);
                 colsum_shared(vacc + VA_B5F, v, ch, lane);
@@ -332,7 +353,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
             // ================================================================================ second-order sweep
             if (second) {
                 // gpe_bar = J (S gx_bar) -> X ; x~_bar += S gx_bar * sum_k d2pe_k gpe_k
-                st_load(st + TS_GPE * kStashPlane, r, ch, h);
+                if (MODE == 1) st_load(st + TS_GPE * kStashPlane, r, ch, h);
                 {
                     const float gb[3] = {T.pv(PV_GXB0)[r] * T.pv(PV_SGN)[r], T.pv(PV_GXB1)[r], T.pv(PV_GXB2)[r]};
                     float curv[3] = {0.f, 0.f, 0.f};
@@ -345,19 +366,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
                 row_store(T.X(), r, ch, v);                                      // X = gpe_bar for the whole sweep
                 // layers 0..3: g_l_bar = A_l gpe_bar (+ B_l q_{l-1}_bar) ; q_l_bar = g_l_bar s_l ; SB_l = g_l_bar q_l ; g_l = q_l s_l
                 //   buffers: q_bar alternates Y, U, Y, U ; g_l always -> Z
+                // Software-pipelined: the GEMMs of layer l + 1 are queued and submitted at the END of layer l's epilogue, then the
+                // SB_l store and the loads of H_{l+1}, Q_{l+1} are issued, then the loop waits.
+                T.gemm(TM_ACC0, T.X(), false);                                   // A0N
+                T.finish();
+                st_load(st + (TS_H + 0) * kStashPlane, r, ch, h);
+                st_load(st + (TS_Q + 0) * kStashPlane, r, ch, w1);
 #pragma unroll 1
                 for (int l = 0; l < 4; ++l) {
                     uint8_t* qprev = (l & 1) ? T.Y() : T.U();                    // q_{l-1}_bar (l >= 1)
                     uint8_t* qcur = (l & 1) ? T.U() : T.Y();
-                    if (l < 3) {
-                        T.gemm(TM_ACC0, T.X(), false);                           // A0N | A1N | A2N
-                        if (l >= 1) T.gemm(TM_ACC0, qprev, true);                // B1N | B2N
-                    } else {
-                        T.gemm(TM_ACC0, qprev, false);                           // W3N
-                    }
-                    st_load(st + (TS_H + l) * kStashPlane, r, ch, h);
-                    st_load(st + (TS_Q + l) * kStashPlane, r, ch, w1);
-                    T.finish_and_load(TM_ACC0, v);
+                    T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                     for (int i = 0; i < NC; ++i) {
                         const float s = sp_slope(h[i]);
@@ -365,64 +384,71 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
                         h[i] = w1[i] * s;                // g_l
                         v[i] = v[i] * s;                 // q_l_bar
                     }
-                    st_store(sc + (TS_SB + l) * kStashPlane, r, ch, w2);
                     row_store(qcur, r, ch, v); row_store(T.Z(), r, ch, h);
-                    // (queued; submitted together with the next phase's layer GEMM)
                     if (l < 3) wgrad(l == 0 ? WG_A0 : (l == 1 ? WG_A1 : WG_A2), T.Z(), T.X());
                     if (l == 1) wgrad(WG_B1, T.Z(), qprev);
                     if (l == 2) wgrad(WG_B2, T.Z(), qprev);
                     if (l == 3) wgrad(WG_W3, T.Z(), qprev);
-                    // Z (g_l) and qprev are re-written in the next iteration's epilogue, i.e. after its finish_and_load,
-                    // whose commit covers these weight-gradient MMAs.
+                    // Z (g_l) and qprev are re-written in the next epilogue, i.e. after its wait_and_load, whose commit covers
+                    // these weight-gradient MMAs.
+                    if (l < 2) { T.gemm(TM_ACC0, T.X(), false); T.gemm(TM_ACC0, qcur, true); }      // A1N, B1N | A2N, B2N
+                    else T.gemm(TM_ACC0, qcur, false);                                              // W3N | W4N (q3_bar is in U)
+                    T.finish();
+                    st_store(sc + (TS_SB + l) * kStashPlane, r, ch, w2);
+                    st_load(st + (TS_H + l + 1) * kStashPlane, r, ch, h);
+                    if (l < 3) st_load(st + (TS_Q + l + 1) * kStashPlane, r, ch, w1);
                 }
-                // layer 4 (q4 = w5): q3_bar is in U
-                T.gemm(TM_ACC0, T.U(), false);                                   // W4N
-                st_load(st + (TS_H + 4) * kStashPlane, r, ch, h);
-                T.finish_and_load(TM_ACC0, v);
+                // layer 4 (q4 = w5)
+                if (MODE == 0) st_load(sc + TS_FB * kStashPlane, r, ch, w1);    // feat_bar, one phase ahead
+                T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) {
                     const float s = sp_slope(h[i]);
                     const float w5 = T.cst[C_W5 + c0 + i];
-                    w2[i] = v[i] * w5;                   // SB4
-                    w1[i] = v[i] * s;                    // -> dw5
+                    w2[i] = v[i] * w5;                   // SB4 (stays in w2 for the first-order sweep)
+                    v[i] = v[i] * s;                     // -> dw5
                     h[i] = w5 * s;                       // g4
                 }
-                st_store(sc + (TS_SB + 4) * kStashPlane, r, ch, w2);
-                colsum_shared(vacc + VA_W5, w1, ch, lane);
+                colsum_shared(vacc + VA_W5, v, ch, lane);
                 row_store(T.Z(), r, ch, h);
                 wgrad(WG_W4, T.Z(), T.U());
+            } else if (MODE == 0) {
+                st_load(sc + TS_FB * kStashPlane, r, ch, w1);
             }
 
             // ================================================================================ first-order sweep
             // a4_bar = (w5 sdf_bar + W5f^T feat_bar) s4 + SB4 t4 -> Y
             if (MODE == 0) {
-                plane_to_act(T, sc + TS_FB * kStashPlane, T.X(), v);           // feat_bar -> X (X = gpe_bar: its readers are done
+                row_store(T.X(), r, ch, w1);                                     // feat_bar -> X (X = gpe_bar: its readers are done
                 T.gemm(TM_ACC0, T.X(), false);                                   //   once the W4N phase above completed)  W5FT
+                T.finish();
                 st_load(st + (TS_H + 4) * kStashPlane, r, ch, h);
-                if (second) st_load(sc + (TS_SB + 4) * kStashPlane, r, ch, w2);
-                T.finish_and_load(TM_ACC0, v);
+                st_load(st + (TS_H + 3) * kStashPlane, r, ch, w1);              // h3, one phase ahead
+                T.wait_and_load(TM_ACC0, v);
             } else {
-                drain_mma();                                                     // mode 1: no GEMM here; retire the weight gradients
+                T.commit(); T.submit();                                          // mode 1: no GEMM here; retire the weight gradients
                 st_load(st + (TS_H + 4) * kStashPlane, r, ch, h);
-                if (second) st_load(sc + (TS_SB + 4) * kStashPlane, r, ch, w2);
+                st_load(st + (TS_H + 3) * kStashPlane, r, ch, w1);
+                T.wait_mma();
 #pragma unroll
                 for (int i = 0; i < NC; ++i) v[i] = 0.f;
             }
             {
                 const float sb = T.pv(PV_SDFB)[r];
+                float dw5[NC];
 #pragma unroll
                 for (int i = 0; i < NC; ++i) {
                     float s, t;
                     sp_slope_curv(h[i], s, t);
                     const float hb = v[i] + T.cst[C_W5 + c0 + i] * sb;
                     v[i] = hb * s + (second ? w2[i] * t : 0.f);      // a4_bar
-                    w1[i] = sb * h[i];                                // -> dw5
+                    dw5[i] = sb * h[i];                               // -> dw5
                 }
                 if (ch == 0) { const float sres = warp_sum(sb); if (lane == 0) atomicAdd(vacc + VA_B5, sres); }
+                colsum_shared(vacc + VA_W5, dw5, ch, lane);
             }
             row_store(T.Y(), r, ch, v);
             colsum_shared(vacc + VA_B4, v, ch, lane);
-            colsum_shared(vacc + VA_W5, w1, ch, lane);
             if (MODE == 0) {
                 row_store(T.Z(), r, ch, h);                                      // h4 -> Z  (Z = g4: weight gradient W4 retired above)
                 wgrad(WG_W5F, T.X(), T.Z());
@@ -434,13 +460,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
                 uint8_t* acur = (l & 1) ? T.Y() : T.X();                         // a_{l+1}_bar
                 uint8_t* anew = (l & 1) ? T.X() : T.Y();                         // a_l_bar
                 uint8_t* hbuf = (l & 1) ? T.U() : T.Z();
-                plane_to_act(T, st + (TS_H + l) * kStashPlane, hbuf, h);        // h_l (h keeps this thread's values)
+#pragma unroll
+                for (int i = 0; i < NC; ++i) h[i] = w1[i];
+                row_store(hbuf, r, ch, h);                                       // h_l (h keeps this thread's values)
                 if (l < 2) { T.gemm(TM_ACC1, acur, false); }                     // A2T | A1T  -> pe_bar
                 T.gemm(TM_ACC0, acur, false);                                    // W4T | W3T | B2T | B1T
                 T.commit();
                 wgrad(l == 3 ? WG_W4 : (l == 2 ? WG_W3 : (l == 1 ? WG_B2 : WG_B1)), acur, hbuf);
                 if (l < 2) wgrad(l == 1 ? WG_A2 : WG_A1, acur, T.P());
+                T.submit();
                 if (second) st_load(sc + (TS_SB + l) * kStashPlane, r, ch, w2);
+                if (l > 0) st_load(st + (TS_H + l - 1) * kStashPlane, r, ch, w1);       // h_{l-1}, one phase ahead
                 T.wait_and_load(TM_ACC0, v);
 #pragma unroll
                 for (int i = 0; i < NC; ++i) {
@@ -452,8 +482,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
                 if (l == 3) colsum_shared(vacc + VA_B3, v, ch, lane);
                 else colsum_global(cbb + (cb_rows + l) * 64, v, ch, lane);
                 if (l < 2) {
-                    tmem_ld_32x16(T.tmem + TM_ACC1 + ((uint32_t)(32 * (T.warp & 3)) << 16) + (uint32_t)c0, w1);
-                    fold_pe_tc(T, w1);
+                    tmem_ld_32x16(T.tmem + TM_ACC1 + ((uint32_t)(32 * (T.warp & 3)) << 16) + (uint32_t)c0, w2);
+                    fold_pe_tc(T, w2);
                 }
             }
             // a0_bar is in Y: dA0 += a0_bar (x) pe ; pe_bar += A0^T a0_bar

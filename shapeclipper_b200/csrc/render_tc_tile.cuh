@@ -53,15 +53,16 @@ struct TileTC {
     __device__ __forceinline__ void submit() {}
 #else
     // ---- role-split kernels (render_tc_bwd.cu): the 16 epilogue warps never issue an MMA. They describe the work as COMMANDS
-    // (thread 0 writes them into a 4-batch ring in shared memory), publish their operand stores (fence.proxy.async, one
-    // mbarrier arrive per warp on ready[batch & 3] — no CTA barrier, nobody waits for the slowest warp) and go on to wait for the
-    // accumulator; a dedicated warp (warp 16) interprets the commands: waits for the weights, issues, commits, prefetches.
+    // (thread 0 writes them into a 4-batch ring in shared memory), publish their operand stores (fence.proxy.async + a NON-BLOCKING
+    // bar.arrive on named barrier 4 + (batch & 1), which the issuing warp bar.sync's on: hardware barrier ordering without a
+    // CTA-wide wait and without the MEMBAR.ALL.CTA a releasing mbarrier.arrive costs — that one waits for every outstanding global
+    // load/store of the thread, i.e. for the prefetched saved planes) and go on to wait for the accumulator; a dedicated warp
+    // (warp 16) interprets the commands: waits for the weights, issues, commits, prefetches.
     // Command word: bits 0-1 op, 2-5 accumulator column / 16 (GEMM) or weight-gradient matrix (WGRAD), 6 accumulate,
     // 7-9 operand buffer A (act[] index), 10-12 operand buffer B (WGRAD). Word 7 of a batch = its length.
-    // At most ONE batch without a COMMIT may be submitted between two batches with one (the epilogue warps wait for every
-    // commit), so the epilogue warps are never more than two batches ahead of the issuer: the ring of four cannot wrap.
+    // EVERY batch ends in work covered by a COMMIT the epilogue warps wait for before they submit the next one, so they are never
+    // more than one batch ahead of the issuer: two barrier ids and a ring of four command slots cannot wrap.
     uint32_t* cmd;              // [kCmdBatches][kCmdWords]
-    uint64_t* ready;            // [kCmdBatches], count 16 (one arrive per epilogue warp)
     uint32_t batch, ncmd;       // uniform over the epilogue warps
     enum : uint32_t { OP_GEMM = 0, OP_COMMIT = 1, OP_WGRAD = 2, OP_END = 3 };
     __device__ __forceinline__ void sync() const { asm volatile("bar.sync 2, 512;" ::: "memory"); }
@@ -80,11 +81,11 @@ struct TileTC {
         if (tid == 0) cmd[(batch & 3u) * kCmdWords + (kCmdWords - 1)] = ncmd;
         sctc::fence_proxy_async();                 // this thread's operand stores -> visible to the tensor core's (async-proxy) reads
         sctc::tc_fence_before();                   // its tcgen05.ld of the accumulator the next MMA may overwrite
-        __syncwarp();
-        if (lane == 0) sctc::mbar_arrive(ready + (batch & 3u));
+        if (batch & 1u) asm volatile("bar.arrive 5, 544;" ::: "memory"); else asm volatile("bar.arrive 4, 544;" ::: "memory");
         ++batch; ncmd = 0;
     }
 #endif
+    __device__ __forceinline__ void finish() { commit(); submit(); }       // then: prefetch loads, wait_and_load()
     __device__ __forceinline__ void finish_and_load(uint32_t acc_col, float (&v)[NC]) { commit(); wait_and_load(acc_col, v); }
     // everyone: wait for the accumulator, then read this thread's NC columns
     __device__ __forceinline__ void wait_mma() {
@@ -415,8 +416,9 @@ __device__ __forceinline__ void tc_tile_forward(TileTC& T, const ScRenderArgs& a
         const uint8_t* src = (j == 3) ? T.X() : ((j == 2) ? T.Z() : ((j == 1) ? T.Y() : T.X()));
         uint8_t* dst = (j == 3) ? T.Z() : ((j == 2) ? T.Y() : ((j == 1) ? T.X() : T.Z()));   // g3->Z g2->Y g1->X g0->Z
         T.gemm(TM_ACC0, src, false);                                                     // W4T | W3T | B2T | B1T
+        T.finish();
         st_load(st + (TS_H + j) * kStashPlane, r, ch, h);
-        T.finish_and_load(TM_ACC0, v);
+        T.wait_and_load(TM_ACC0, v);
         if (STASH_ALL) st_store(st + (TS_Q + j) * kStashPlane, r, ch, v);
 #pragma unroll
         for (int i = 0; i < NC; ++i) v[i] *= sp_slope(h[i]);
