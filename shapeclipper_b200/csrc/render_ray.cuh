@@ -1,6 +1,6 @@
 // render_ray.cuh — compositing forward + adjoint of one tile's rays (renderer.py:115-152,187-209 and its autograd),
 // generic over the tile type (FFMA Tile / tensor-core TileTC: both expose pv(), ray, tid, lane, warp, S, first, b, beta,
-// rays_per_tile). Inputs: per-point vectors Z, SIG, CF, UN, NS*, COL*, GX*, SDF. Outputs: SDFB, GXB*, CB* (colour adjoint),
+// rays_per_tile, sync() = barrier over the executing threads, scan_sync() = barrier over the threads that own a sample). Inputs: per-point vectors Z, SIG, CF, UN, NS*, COL*, GX*, SDF. Outputs: SDFB, GXB*, CB* (colour adjoint),
 // ZB (partial), depth_fac_bar (global), beta adjoint (atomicAdd into `beta_acc`). Executed by all threads of the CTA; only
 // the first 128 own a sample. Algorithm: tests/kernel_model.py::composite_backward.
 #pragma once
@@ -24,9 +24,9 @@ __device__ __forceinline__ float ray_scan_t(const TT& T, float v, float& total) 
     }
     total = __shfl_sync(0xffffffffu, incl, seg - 1, seg);
     if (S > 32) {
-        asm volatile("bar.sync 1, 128;");
+        T.scan_sync();
         if (T.lane == 31) T.ray[T.warp] = incl;
-        asm volatile("bar.sync 1, 128;");
+        T.scan_sync();
         const int w0 = (p / S) * (S / 32), w1 = w0 + S / 32;
         float before = 0.f, tot = 0.f;
         for (int ww = w0; ww < w1; ++ww) { const float t = T.ray[ww]; tot += t; if (ww < T.warp) before += t; }
@@ -158,7 +158,7 @@ __device__ __forceinline__ void ray_phase_backward(TT& T, const ScRenderArgs& a,
                     const float sigma_bar = E_bar * delta;
                     const float delta_bar = (s < S - 1) ? E_bar * sigma : 0.f;
                     T.pv(PV_TMP)[p] = delta_bar;
-                    asm volatile("bar.sync 1, 128;");
+                    T.scan_sync();
                     z_bar -= delta_bar;
                     if (s > 0) z_bar += T.pv(PV_TMP)[p - 1];
                     T.pv(PV_ZB)[p] = z_bar;

@@ -6,9 +6,10 @@
 // MN-major) that accumulates into one of 12 TMEM-resident matrices for the WHOLE kernel and is never waited for,
 // except before its operand buffers are overwritten. Vector gradients accumulate in shared memory. One flush at the end.
 //
-// Roles (640 threads): warps 0-15 = epilogue warps (TMEM lane quarter = warp & 3, column group = warp >> 2), warp 16 = MMA issuer
-// (interprets the command ring: weights, tcgen05.mma, commits, weight prefetch), warps 17-19 pad the issuer's warpgroup
-// (setmaxnreg works on warpgroups). With the issue code on warp 0 — also an epilogue warp — every phase waited for warp 0 to get
+// Roles (608 threads = 19 warps: five per scheduler is the most that leaves 96 registers a thread): warps 0-15 = epilogue warps
+// (TMEM lane quarter = warp & 3, column group = warp >> 2); warps 16-17 = ray group (saved-activation mode: loads the NEXT tile's saved
+// per-point vectors and upstream adjoints and runs its compositing adjoint, 64 points at a time, while the epilogue warps sweep the
+// current tile - latency-bound work of 128 threads that used to sit in front of every tile); warp 18 = MMA issuer (interprets the command ring: weights, tcgen05.mma, commits, weight prefetch). With the issue code on warp 0 — also an epilogue warp — every phase waited for warp 0 to get
 // through 12-60 MMA issues (blocking on the tensor pipe's queue) AND its own epilogue before the next CTA barrier: clock64 trace,
 // 2-4 k cycles of a ~7 k-cycle phase. Now no epilogue warp ever waits for another one inside the sweeps.
 #include <cuda_runtime.h>
@@ -93,8 +94,26 @@ __device__ __forceinline__ void fold_pe_tc(const TileTC& T, const float (&v)[NC]
     }
 }
 
-constexpr int kBwdThreads = 640;         // 16 epilogue warps + the issuer's warpgroup
-constexpr int kIssuerWarp = 16;
+constexpr int kBwdThreads = 608;         // 16 epilogue warps + 2 ray warps + the issuer
+constexpr int kRayWarp0 = 16, kIssuerWarp = 18, kRayThreads = 64;
+
+// What ray_phase_backward / saved_vectors need of a tile, for the ray group: its 64 threads take the tile as two half tiles of 64
+// points (whole rays: S <= 64), `half` selects the one in flight.
+// Its input vectors (Z', SIG, CF, UN, GX*, NS*, COL*, SDF, W, TMP) are private to the group in saved-activation mode; the eight
+// output vectors go to slot `out_shift` (see TileTC::pv). Z' is the group's own copy of the sample depths (the epilogue warps'
+// PV_Z belongs to the tile they are sweeping).
+struct RayTile {
+    float *pt, *ray;
+    int tid, lane, warp, S, first, b, rays_per_tile, out_shift, half;
+    float beta;
+    __device__ __forceinline__ float* pv(int v) const {
+        const int u = (v == PV_Z) ? PX_A + 8 : v + ((v >= PV_SDFB && v <= PV_ZB) ? out_shift : 0);
+        return pt + u * M_TILE + kRayThreads * half;
+    }
+    __device__ __forceinline__ void sync() const { asm volatile("bar.sync 3, 64;" ::: "memory"); }
+    __device__ __forceinline__ void scan_sync() const { asm volatile("bar.sync 3, 64;" ::: "memory"); }
+    __device__ __forceinline__ void mark() const {}
+};
 
 // The issuing warp (all 32 lanes; one elected lane executes the tcgen05 instructions): interprets the command batches.
 template <int PREC>
@@ -136,7 +155,8 @@ __device__ __forceinline__ void issuer_loop(WeightRing& wr, const uint32_t* cmd,
     wg_mask_out = wg_init;
 }
 
-template <int MODE, int PREC>      // PREC = ScRenderArgs::precision, compile-time (see render_tc.cu)
+// PREC = ScRenderArgs::precision, SAVED = mode 0 with the activations saved by sc_render_tc_forward (no recompute): compile-time
+template <int MODE, int PREC, bool SAVED>
 __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScRenderArgs a, float* stash_base)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -150,12 +170,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
     uint32_t* cmd = reinterpret_cast<uint32_t*>(smem + SMB_CMD);
 
     const bool second = (MODE == 0) || (a.want_grad && a.grad_bar != nullptr);
-    const bool use_saved = (MODE == 0) && a.saved != nullptr;      // activations saved by sc_render_tc_forward: no recompute
+    constexpr bool use_saved = SAVED;
     float* part = a.grad_partial + (size_t)blockIdx.x * kGradFloats;
     for (int i = threadIdx.x; i < kGradFloats; i += kBwdThreads) part[i] = 0.f;
     for (int i = threadIdx.x; i < VA_FLOATS; i += kBwdThreads) vacc[i] = 0.f;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 9; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(bars + BAR_RAY_FULL + i, kRayThreads); mbar_init(bars + BAR_RAY_FREE + i, 512); }
         mbar_fence_init();
         int len; build_seq_tc_bwd(seq, len, MODE, second, !use_saved); seq_len = len;
     }
@@ -179,13 +200,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
     const uint32_t tmem_base = *tmem_slot;
     const int warp_id = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform for the compiler too
 
-    if (warp_id >= kIssuerWarp) {
-        // ---------------------------------------------------------------------------------------- the issuer's warpgroup
-        // register budget: 640 x 96 at launch; setmaxnreg.inc can only take what a .dec has RELEASED into the CTA's pool (the SM's
-        // unallocated registers are not part of it: asking for more than was released blocks forever): 128 x 32 released here =
-        // 512 x 8 taken by the epilogue warps
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-        if (warp_id == kIssuerWarp && active) {
+    if (warp_id == kIssuerWarp) {
+        // ---------------------------------------------------------------------------------------- the issuer (keeps its 96 registers)
+        if (active) {
             WeightRing wr;
             wr.blob = blob; wr.slots = smem + SMB_W_BWD; wr.wfull = bars + BAR_WFULL; wr.wfree = bars + BAR_WFREE;
             wr.seq = seq; wr.seq_len = seq_len; wr.NS = 2; wr.w0 = true;
@@ -197,14 +214,57 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
         __syncthreads();                  // (B) the epilogue warps have flushed TMEM
         return;
     }
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-
+    if (warp_id >= kRayWarp0) {
+        // ---------------------------------------------------------------------------------------- the ray group
+        // (No setmaxnreg: 19 warps x 96 registers fit and the epilogue warps need no more. Learnt on the way: setmaxnreg.inc can only
+        // take what a .dec has RELEASED into the CTA's pool - the SM's unallocated registers are not part of it, asking for more
+        // blocks forever; and the register file is per scheduler: a sixth warp on one of them, 21 warps, means 80 registers.)
+        if (SAVED && active) {
+            RayTile R;
+            float* f = reinterpret_cast<float*>(smem + SMB_F32);
+            R.pt = f + SF_PT; R.ray = f + SF_RAY;
+            R.tid = threadIdx.x - 32 * kRayWarp0; R.lane = threadIdx.x & 31; R.warp = R.tid >> 5;
+            R.S = a.n_samples; R.rays_per_tile = kRayThreads / a.n_samples;
+            R.beta = fabsf(*a.beta_param) + a.beta_min;
+            const int tiles_per_image_ = (a.n_per_image + per_tile_ - 1) / per_tile_;
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_; tile += gridDim.x, ++it) {
+                const uint32_t slot = it & 1u;
+                mbar_wait(bars + BAR_RAY_FREE + slot, ((it >> 1) & 1u) ^ 1u);        // the epilogue warps are done with this slot
+                R.b = tile / tiles_per_image_;
+                R.out_shift = slot ? (PX_A - PV_SDFB) : 0;
+                const float* plane = reinterpret_cast<const float*>(a.saved) + ((size_t)tile * TS_SAVED_PLANES + TS_SAVED_PV) * kStashPlane;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    R.half = half;
+                    R.first = (tile % tiles_per_image_) * per_tile_ + half * R.rays_per_tile;
+                    const int p = R.tid, rr = R.first + p / R.S;
+                    R.pv(PV_Z)[p] = (rr < a.n_per_image) ? tc_sample_depth(a, R.b, rr, p % R.S, R.S) : 0.f;
+                    saved_vectors<false>(R, const_cast<float*>(plane) + kRayThreads * half);
+                    R.sync();
+                    ray_phase_backward(R, a, vacc + VA_BETA, kRayThreads);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {                                     // o3_bar = colour_bar * col (1 - col)
+                        const float col = R.pv(PV_COL0 + c)[p];
+                        const float vv = R.pv(PV_CB0 + c)[p] * col * (1.f - col);
+                        R.pv(PV_CB0 + c)[p] = vv;
+                        const float sres = warp_sum(vv);
+                        if (R.lane == 0) atomicAdd(vacc + VA_C3R + c, sres);
+                    }
+                }
+                sctc::mbar_arrive(bars + BAR_RAY_FULL + slot);                        // (release) the slot's vectors are complete
+            }
+        }
+        __syncthreads();                  // (A)
+        __syncthreads();                  // (B)
+        return;
+    }
     TileTC T;
     {   // same carve-up as the forward kernel, but 5 operand buffers + 2 weight slots
         for (int i = 0; i < kNumAct; ++i) T.act[i] = smem + SMB_ACT + i * kActBytes;
         float* f = reinterpret_cast<float*>(smem + SMB_F32);
         T.cst = f + SF_CONST; T.cb = f + SF_CB; T.pt = f + SF_PT; T.ray = f + SF_RAY; T.bias = f + SF_BIAS;
-        T.cmd = cmd; T.batch = 0; T.ncmd = 0;
+        T.cmd = cmd; T.batch = 0; T.ncmd = 0; T.out_shift = 0;
         T.mma_done = bars + BAR_MMA_DONE; T.mma_phase = 0;
         T.tid = threadIdx.x; T.lane = threadIdx.x & 31; T.warp = threadIdx.x >> 5;
         T.w0 = false;
@@ -234,7 +294,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
     float v[NC], h[NC], w1[NC], w2[NC];
 
     if (active) {
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        uint32_t tile_it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tile_it) {
             T.b = tile / tiles_per_image;
             T.first = (tile % tiles_per_image) * per_tile;
             float* cbb = a.cb_bar + (size_t)T.b * kCbRows * 64;
@@ -244,13 +305,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
             T.mark();                                                            // [trace] setup done
             if (use_saved) {
                 st = reinterpret_cast<float*>(a.saved) + (size_t)tile * TS_SAVED_PLANES * kStashPlane;
-                if (MODE == 0) {                                                 // r2, r1: consumed after the ray phase, HBM latency hidden
-                    st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);
-                    st_load(st + (TS_R + 1) * kStashPlane, r, ch, w1);
-                }
-                saved_vectors<false>(T, st + TS_SAVED_PV * kStashPlane);
-                T.sync();
-                T.mark();                                                        // [trace] saved vectors loaded
+                st_load(st + (TS_R + 2) * kStashPlane, r, ch, h);               // r2, r1: one phase ahead
+                st_load(st + (TS_R + 1) * kStashPlane, r, ch, w1);
             } else {
                 tc_tile_forward<MODE, true>(T, a, second, MODE == 0);
             }
@@ -268,22 +324,31 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
                 }
                 T.sync();
             } else {
-                ray_phase_backward(T, a, vacc + VA_BETA, 512);
-                T.mark();                                                        // [trace] ray phase done
+                if (use_saved) {
+                    // the ray group prepared this tile's SDFB, GXB*, CB* (already x col (1 - col)), ZB while the previous tile was swept
+                    const uint32_t slot = tile_it & 1u;
+                    T.out_shift = slot ? (PX_A - PV_SDFB) : 0;
+                    mbar_wait(bars + BAR_RAY_FULL + slot, (tile_it >> 1) & 1u);
+                    T.sync();
+                    T.mark();                                                    // [trace] ray vectors ready
+                } else {
+                    ray_phase_backward(T, a, vacc + VA_BETA, 512);
+                    T.mark();                                                    // [trace] ray phase done
 
-                // ============================================================================ RGB backward
-                if (tid < M_TILE) {                                  // o3_bar = colour_bar * col (1 - col)
+                    // ======================================================================== RGB backward
+                    if (tid < M_TILE) {                              // o3_bar = colour_bar * col (1 - col)
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float col = T.pv(PV_COL0 + c)[tid];
-                        const float vv = T.pv(PV_CB0 + c)[tid] * col * (1.f - col);
-                        T.pv(PV_CB0 + c)[tid] = vv;
-                        const float sres = warp_sum(vv);
-                        if (lane == 0) atomicAdd(vacc + VA_C3R + c, sres);
+                        for (int c = 0; c < 3; ++c) {
+                            const float col = T.pv(PV_COL0 + c)[tid];
+                            const float vv = T.pv(PV_CB0 + c)[tid] * col * (1.f - col);
+                            T.pv(PV_CB0 + c)[tid] = vv;
+                            const float sres = warp_sum(vv);
+                            if (lane == 0) atomicAdd(vacc + VA_C3R + c, sres);
+                        }
                     }
+                    T.sync();
+                    T.mark();                                                    // [trace] o3_bar done
                 }
-                T.sync();
-                T.mark();                                                        // [trace] o3_bar done
                 // o2_bar = (V3^T o3_bar) * [r2 > 0] -> Y ; dV3 += o3_bar (x) r2
                 // Every activation plane is loaded ONE PHASE AHEAD of its use (into w1, between the submit and the wait of the phase
                 // before): a load issued right where the plane is needed costs a full L2/HBM round trip per phase, and nothing hides
@@ -530,11 +595,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
                     atomicAdd(a.scale_dist_bar + T.b, a.cam_dist * vv[6]);
                 }
             }
+            if (use_saved) sctc::mbar_arrive(bars + BAR_RAY_FREE + (tile_it & 1u));      // this slot's vectors may be overwritten
         }
         T.commit(); T.end();                 // retire every MMA, then let the issuer drain its weight ring and publish wg_mask
         T.wait_mma();
     }
-    __syncthreads();                         // (A) all 640 threads
+    __syncthreads();                         // (A) all threads
     if (active) {
         // ---- flush: 12 TMEM-resident weight gradients + the shared vector accumulators -> this CTA's partial
         const int goff[NWG] = {G_A0, G_A1, G_A2, G_B1, G_B2, G_W3, G_W4, G_W5F, G_V0P, G_V0F, G_V1, G_V2};
@@ -578,13 +644,15 @@ extern "C" int sc_render_tc_backward(const ScRenderArgs* a, cudaStream_t stream)
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t err;
-#define SC_LAUNCH_BWD(MODE_, PREC_) do { \
-        err = cudaFuncSetAttribute(render_tc_bwd_kernel<MODE_, PREC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc); \
+#define SC_LAUNCH_BWD(MODE_, PREC_, SAVED_) do { \
+        err = cudaFuncSetAttribute(render_tc_bwd_kernel<MODE_, PREC_, SAVED_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytesTc); \
         if (err != cudaSuccess) return (int)err; \
-        render_tc_bwd_kernel<MODE_, PREC_><<<sms, sct::kBwdThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch); } while (0)
-    const bool single = a->precision == 1;
-    if (a->mode == 0) { if (single) SC_LAUNCH_BWD(0, 1); else SC_LAUNCH_BWD(0, 0); }
-    else { if (single) SC_LAUNCH_BWD(1, 1); else SC_LAUNCH_BWD(1, 0); }
+        render_tc_bwd_kernel<MODE_, PREC_, SAVED_><<<sms, sct::kBwdThreads, kSmemBytesTc, stream>>>(*a, (float*)a->scratch); } while (0)
+    const bool single = a->precision == 1, saved = a->mode == 0 && a->saved != nullptr && a->n_samples <= 64;      // ray group: whole rays per half tile
+    if (a->mode == 0) {
+        if (saved) { if (single) SC_LAUNCH_BWD(0, 1, true); else SC_LAUNCH_BWD(0, 0, true); }
+        else { if (single) SC_LAUNCH_BWD(0, 1, false); else SC_LAUNCH_BWD(0, 0, false); }
+    } else { if (single) SC_LAUNCH_BWD(1, 1, false); else SC_LAUNCH_BWD(1, 0, false); }
 #undef SC_LAUNCH_BWD
     return (int)cudaGetLastError();
 }

@@ -26,7 +26,16 @@ struct TileTC {
 #else
     __device__ __forceinline__ void mark() {}
 #endif
+#ifdef SC_TC_ROLE_SPLIT
+    // the eight vectors the ray group hands over (SDFB, GXB*, CB*, ZB) are double-buffered: slot 1 lives in the PX_* scratch
+    int out_shift;              // 0 or PX_A - PV_SDFB
+    __device__ __forceinline__ float* pv(int v) const {
+        return pt + (v + ((v >= scr::PV_SDFB && v <= scr::PV_ZB) ? out_shift : 0)) * M_TILE;
+    }
+#else
     __device__ __forceinline__ float* pv(int v) const { return pt + v * M_TILE; }
+#endif
+    __device__ __forceinline__ void scan_sync() const { asm volatile("bar.sync 1, 128;" ::: "memory"); }
     __device__ __forceinline__ uint8_t* P() const { return act[0]; }
     __device__ __forceinline__ uint8_t* X() const { return act[1]; }
     __device__ __forceinline__ uint8_t* Y() const { return act[2]; }
@@ -119,8 +128,8 @@ constexpr int TS_H = 0, TS_Q = 5, TS_FEAT = 9, TS_R = 10, TS_GPE = 13, TS_FB = 1
 constexpr int TS_SAVED_PV = 14, TS_SAVED_PLANES = 15;
 constexpr int kSavedVecs = 13;
 // forward (store = true): per-point vectors the backward needs -> plane TS_SAVED_PV of the tile's saved block; backward: back.
-template <bool STORE>
-__device__ __forceinline__ void saved_vectors(const TileTC& T, float* plane) {
+template <bool STORE, class TT>
+__device__ __forceinline__ void saved_vectors(const TT& T, float* plane) {
     constexpr int vecs[kSavedVecs] = {scr::PV_SDF, scr::PV_COL0, scr::PV_COL1, scr::PV_COL2, scr::PV_GX0, scr::PV_GX1, scr::PV_GX2,
                                       scr::PV_SIG, scr::PV_CF, scr::PV_UN, scr::PV_NS0, scr::PV_NS1, scr::PV_NS2};
     if (T.tid < M_TILE) {
@@ -254,6 +263,24 @@ __device__ __forceinline__ void posenc_cols(const float (&xt)[3], float (&v)[NC]
     }
 }
 
+// depth of sample s of ray r (image b), exactly as the reference builds it (model/renderer.py:80-96): stratified bins, jitter inside
+__device__ __forceinline__ float tc_sample_depth(const ScRenderArgs& a, int b, int r, int s, int S) {
+    const float c = __fmul_rn(a.cam_dist, a.scale_dist[b]);
+    const float nr = __fsub_rn(c, a.half_range), fr = __fadd_rn(c, a.half_range);
+    auto zb = [&](int i) {
+        const float t = a.t_vals[i];
+        return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.f, t)), __fmul_rn(fr, t));
+    };
+    float z = zb(s);
+    if (a.jitter != nullptr) {
+        const float up = (s < S - 1) ? __fmul_rn(0.5f, __fadd_rn(zb(s + 1), z)) : z;
+        const float lo = (s > 0) ? __fmul_rn(0.5f, __fadd_rn(z, zb(s - 1))) : z;
+        const float u = a.jitter[((size_t)b * a.n_per_image + r) * S + s];
+        z = __fadd_rn(lo, __fmul_rn(__fsub_rn(up, lo), u));
+    }
+    return z;
+}
+
 template <int MODE>
 __device__ __forceinline__ void tc_tile_setup(const TileTC& T, const ScRenderArgs& a)
 {
@@ -268,19 +295,7 @@ __device__ __forceinline__ void tc_tile_setup(const TileTC& T, const ScRenderArg
         const int r = T.first + p / S, s = p % S;
         valid = r < R;
         if (valid) {
-            const float c = __fmul_rn(a.cam_dist, a.scale_dist[T.b]);
-            const float nr = __fsub_rn(c, a.half_range), fr = __fadd_rn(c, a.half_range);
-            auto zb = [&](int i) {
-                const float t = a.t_vals[i];
-                return __fadd_rn(__fmul_rn(nr, __fsub_rn(1.f, t)), __fmul_rn(fr, t));
-            };
-            z = zb(s);
-            if (a.jitter != nullptr) {
-                const float up = (s < S - 1) ? __fmul_rn(0.5f, __fadd_rn(zb(s + 1), z)) : z;
-                const float lo = (s > 0) ? __fmul_rn(0.5f, __fadd_rn(z, zb(s - 1))) : z;
-                const float u = a.jitter[((size_t)T.b * R + r) * S + s];
-                z = __fadd_rn(lo, __fmul_rn(__fsub_rn(up, lo), u));
-            }
+            z = tc_sample_depth(a, T.b, r, s, S);
             const float* d = a.ray_dirs + ((size_t)T.b * R + r) * 3;
             const float* o = a.cam_loc + (size_t)T.b * 3;
             x0 = __fadd_rn(o[0], __fmul_rn(z, d[0]));
