@@ -176,7 +176,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
     for (int i = threadIdx.x; i < VA_FLOATS; i += kBwdThreads) vacc[i] = 0.f;
     if (threadIdx.x == 0) {
         for (int i = 0; i < 9; ++i) mbar_init(bars + i, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(bars + BAR_RAY_FULL + i, kRayThreads); mbar_init(bars + BAR_RAY_FREE + i, 512); }
         mbar_fence_init();
         int len; build_seq_tc_bwd(seq, len, MODE, second, !use_saved); seq_len = len;
     }
@@ -230,7 +229,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total_; tile += gridDim.x, ++it) {
                 const uint32_t slot = it & 1u;
-                mbar_wait(bars + BAR_RAY_FREE + slot, ((it >> 1) & 1u) ^ 1u);        // the epilogue warps are done with this slot
+                // hand-over through named barriers (6 + slot: slot free, 8 + slot: slot full; 512 + 64 threads): hardware barrier
+                // ordering without the MEMBAR.ALL.CTA of a releasing mbarrier arrive, which would make every epilogue thread wait for
+                // its global atomics at the end of each tile
+                if (it >= 2) { if (slot) asm volatile("bar.sync 7, 576;" ::: "memory"); else asm volatile("bar.sync 6, 576;" ::: "memory"); }
                 R.b = tile / tiles_per_image_;
                 R.out_shift = slot ? (PX_A - PV_SDFB) : 0;
                 const float* plane = reinterpret_cast<const float*>(a.saved) + ((size_t)tile * TS_SAVED_PLANES + TS_SAVED_PV) * kStashPlane;
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
                         if (R.lane == 0) atomicAdd(vacc + VA_C3R + c, sres);
                     }
                 }
-                sctc::mbar_arrive(bars + BAR_RAY_FULL + slot);                        // (release) the slot's vectors are complete
+                if (slot) asm volatile("bar.arrive 9, 576;" ::: "memory"); else asm volatile("bar.arrive 8, 576;" ::: "memory");   // slot full
             }
         }
         __syncthreads();                  // (A)
@@ -328,8 +330,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
                     // the ray group prepared this tile's SDFB, GXB*, CB* (already x col (1 - col)), ZB while the previous tile was swept
                     const uint32_t slot = tile_it & 1u;
                     T.out_shift = slot ? (PX_A - PV_SDFB) : 0;
-                    mbar_wait(bars + BAR_RAY_FULL + slot, (tile_it >> 1) & 1u);
-                    T.sync();
+                    if (slot) asm volatile("bar.sync 9, 576;" ::: "memory"); else asm volatile("bar.sync 8, 576;" ::: "memory");
                     T.mark();                                                    // [trace] ray vectors ready
                 } else {
                     ray_phase_backward(T, a, vacc + VA_BETA, 512);
@@ -595,7 +596,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) render_tc_bwd_kernel(const ScR
                     atomicAdd(a.scale_dist_bar + T.b, a.cam_dist * vv[6]);
                 }
             }
-            if (use_saved) sctc::mbar_arrive(bars + BAR_RAY_FREE + (tile_it & 1u));      // this slot's vectors may be overwritten
+            if (use_saved && tile + 2 * (int)gridDim.x < total) {                        // this slot's vectors may be overwritten
+                if (tile_it & 1u) asm volatile("bar.arrive 7, 576;" ::: "memory"); else asm volatile("bar.arrive 6, 576;" ::: "memory");
+            }
         }
         T.commit(); T.end();                 // retire every MMA, then let the issuer drain its weight ring and publish wg_mask
         T.wait_mma();
