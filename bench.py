@@ -21,6 +21,7 @@ bounded sample of the same workload, CLIP leg included (architecture twin, oracl
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -366,7 +367,9 @@ def measure_train_step(a, opt, batch_size, steps, warmup, rank, world, dev, clip
         kernel_ms = {k: tuple(v) for k, v in acc.items()}
     rn.TIMERS.enabled = False
 
-    # ---- end to end through the public API: pinned host batch -> device, step, loss back to the host
+    # ---- end to end through the public API: pinned host batch -> device, step, loss back to the host, EVERY step.
+    # (a) serial: copy, step, read the loss, one after the other; (b) TrainStep.run_epoch, the loop a prefetching loader gives
+    # (model/runner.py:198-225): the same copies and reads, batch i+1 in flight while step i runs. (b) is the e2e figure.
     def e2e_step(i):
         step.load(batches[i % len(batches)])
         if clip_ctx is not None:
@@ -375,7 +378,12 @@ def measure_train_step(a, opt, batch_size, steps, warmup, rank, world, dev, clip
         return float(loss["all"].detach())         # device -> host read of the result
     for i in range(3):
         e2e_step(i)
-    ms_e2e = timed(e2e_step, steps)
+    ms_e2e_serial = timed(e2e_step, steps)
+    extra = (lambda i: [(clip_ctx.static_images, clip_ctx.host_images[i % 2])]) if clip_ctx is not None else None
+    step.run_epoch(batches, 3, extra=extra)
+    e2e_losses = []
+    ms_e2e = timed(lambda i: e2e_losses.extend(step.run_epoch(batches, steps, extra=extra)), 1) / steps
+    assert len(e2e_losses) == steps and all(math.isfinite(v) for v in e2e_losses), "run_epoch must return one finite loss per step"
 
     # ---- the flat gradient all-reduce alone (N > 1): algorithm bandwidth and ring bus bandwidth 2 (N-1)/N x bytes / t
     allreduce = None
@@ -422,7 +430,11 @@ def measure_train_step(a, opt, batch_size, steps, warmup, rank, world, dev, clip
                                     unit="TFLOP/s"))
     images = batch_size * world
     res = dict(value=images / (ms_step * 1e-3), ms_per_step=ms_step,
-               e2e=dict(value=images / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4),
+               e2e=dict(value=images / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e, h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=4,
+                        api="TrainStep.run_epoch: every step's batch copied from pinned host memory and every step's loss read on the host, "
+                            "batch i+1 in flight while step i runs",
+                        serial=dict(value=images / (ms_e2e_serial * 1e-3), ms_per_step=ms_e2e_serial,
+                                    note="the same copies and reads strictly one after the other (load, step, float(loss))")),
                gpu_launches=launches, clocks=clocks, roofline=roofline, allreduce=allreduce, clip=clip_ctx is not None)
     del step, graph, optim, flat, clip_ctx, resident, batches
     rn.invalidate_blob_cache()

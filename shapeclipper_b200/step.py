@@ -62,6 +62,63 @@ class TrainStep:
             for k, t in batch.items():
                 self.var[k].copy_(t, non_blocking=True)
 
+    def run_epoch(self, batches, n_steps=None, extra=None):
+        """Runner.train_epoch's loop (model/runner.py:198-225: `batch = next(loader); var = move_to_device(batch); loss =
+        train_iteration(...)`, the progress bar reading `loss.all` on the host every iteration) over pinned host batches,
+        software-pipelined the way a prefetching loader would be: batch i+1 travels host -> device (a staging copy, on a copy
+        stream) while step i runs, and the loss of step i-1 is read on the host while step i runs. Every step's inputs are copied
+        and every step's loss is read; nothing is skipped, only overlapped.
+        batches: sequence of host batches (cycled); extra: optional callable i -> [(device_tensor, pinned_host_tensor), ...] of
+        further per-step inputs (bench.py: the CLIP leg's images). Returns the list of loss.all values (python floats)."""
+        n = len(batches) if n_steps is None else int(n_steps)
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_pipe", None) is None:
+            self._pipe = dict(copy=torch.cuda.Stream(self.device), staging=[{}, {}],
+                              h2d=[torch.cuda.Event(), torch.cuda.Event()], loaded=[torch.cuda.Event(), torch.cuda.Event()],
+                              read=[torch.cuda.Event(), torch.cuda.Event()],
+                              loss=[torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)])
+        P = self._pipe
+
+        def pairs(i):
+            b = batches[i % len(batches)]
+            out = [(self.var[k], t) for k, t in b.items()]
+            return out + (list(extra(i)) if extra is not None else [])
+
+        def stage(i, slot):
+            P["copy"].wait_event(P["loaded"][slot])            # the step that last consumed this slot has taken its copy
+            with torch.cuda.stream(P["copy"]), torch.no_grad():
+                for dst, src in pairs(i):
+                    buf = P["staging"][slot].get(id(dst))
+                    if buf is None:
+                        buf = P["staging"][slot][id(dst)] = torch.empty_like(dst.detach())
+                    buf.copy_(src, non_blocking=True)
+            P["h2d"][slot].record(P["copy"])
+
+        losses = []
+        for ev in P["loaded"]:
+            ev.record(main)
+        if n > 0:
+            stage(0, 0)
+        for i in range(n):
+            slot = i & 1
+            if i + 1 < n:
+                stage(i + 1, slot ^ 1)
+            main.wait_event(P["h2d"][slot])
+            with torch.no_grad():
+                for dst, _ in pairs(i):
+                    dst.copy_(P["staging"][slot][id(dst)], non_blocking=True)
+            P["loaded"][slot].record(main)
+            loss = self()
+            P["loss"][slot].copy_(loss["all"].detach().reshape(1), non_blocking=True)
+            P["read"][slot].record(main)
+            if i >= 1:
+                P["read"][slot ^ 1].synchronize()
+                losses.append(float(P["loss"][slot ^ 1]))
+        if n > 0:
+            P["read"][(n - 1) & 1].synchronize()
+            losses.append(float(P["loss"][(n - 1) & 1]))
+        return losses
+
     def _forward_backward(self):
         self.flat.zero()
         for k in GRAD_LEAVES:

@@ -138,3 +138,39 @@ def test_eager_render_sees_weights_updated_by_graph_replays():
     assert float((after - before).abs().max()) > 0, "eager SDF query still uses the weights from before the replays"
     rn.invalidate_blob_cache()
     assert torch.equal(after, level())                     # equals a render from freshly packed weights
+
+
+def test_run_epoch_pipelined_equals_serial_loop():
+    """TrainStep.run_epoch (prefetched host batches, delayed loss read) walks the same steps as the serial loop
+    load -> step -> float(loss): same parameters, optimiser state and generator state at the start => the same losses
+    (graph replays are deterministic) and the same final parameters."""
+    from shapeclipper_b200 import synthetic
+    step, params, _ = _make(True)
+    batches = [synthetic.make_batch(step.opt, 4, seed=20 + i) for i in range(3)]
+    p0 = [p.detach().clone() for p in params]
+    st0 = [{k: v.detach().clone() for k, v in st.items()} for st in step.optim.state.values()]
+
+    def restart():
+        with torch.no_grad():
+            for p, q in zip(params, p0):
+                p.copy_(q)
+            for st, s0 in zip(step.optim.state.values(), st0):
+                for k in st:
+                    st[k].copy_(s0[k])
+        torch.cuda.manual_seed(123)
+
+    restart()
+    serial = []
+    for i in range(5):
+        step.load(batches[i % 3])
+        serial.append(float(step()["all"]))
+    p_serial = [p.detach().clone() for p in params]
+    restart()
+    piped = step.run_epoch(batches, 5)
+    torch.cuda.synchronize()
+    assert len(piped) == 5
+    assert piped == pytest.approx(serial, rel=1e-6, abs=1e-7), (piped, serial)
+    for a, b in zip(params, p_serial):             # (atomics in the gradient sums: equal up to summation order)
+        assert float((a.detach() - b).abs().max()) <= 1e-5 + 1e-4 * float(b.abs().max())
+    assert len(set(piped)) > 1          # the batches differ, so do the losses
+    assert step.run_epoch(batches, 0) == []
