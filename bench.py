@@ -36,8 +36,10 @@ UNIT = "images/s"
 FLOP_FWD_PER_POINT = 199424.0       # SURVEY.md §8d convention: 2*(40320 SDF + 40320 grad-SDF + 19072 RGB)
 FLOP_BWD_PER_POINT = 398848.0       # train fwd+bwd = 3x fwd  ->  backward kernel = 2x fwd
 GRAPH_PARAMS = 36800589             # parameters of the reference Graph (flat all-reduce size)
-RENDER_BWD_DRAM_BYTES = 2462139000  # dram__bytes_read.sum + dram__bytes_write.sum of one render_tc_bwd_kernel<0> launch at this shape
-                                    # (ncu --set full, profiles/r01h_render_tc_bwd_ncu_summary.txt: 1.93 GB of saved activations read)
+# dram__bytes_read.sum + dram__bytes_write.sum of one render_tc_bwd_kernel<0, 0, 1> launch (ncu --set full, 512 rays x 64 samples,
+# profiles/r02n_render_tc_b{16,32}_ncu_summary.txt), by images per launch: the saved activations read back (3.75 KB per sample point)
+# plus the L2 write-back of the per-CTA scratch planes
+RENDER_BWD_DRAM_BYTES = {16: 1931685000 + 393357000, 32: 3863811000 + 762239000}
 
 
 def parse():
@@ -409,8 +411,10 @@ def measure_train_step(a, opt, batch_size, steps, warmup, rank, world, dev, clip
     saved = rn.saved_buffer_bytes(batch_size, R, S)
     roofline = dict(kernel="render_tc_bwd_kernel<0>", bound="tensor", achieved=achieved, peak=pk["bf16_sustained"], unit="TFLOP/s",
                     frac=achieved / pk["bf16_sustained"],
-                    traffic=(RENDER_BWD_DRAM_BYTES if (batch_size == 16 and R == 512 and S == 64 and saved) else None),
-                    traffic_note="dram__bytes_read.sum + dram__bytes_write.sum of one launch at batch 16 (ncu --set full, profiles/); null at other shapes",
+                    traffic=(RENDER_BWD_DRAM_BYTES.get(batch_size) if (R == 512 and S == 64 and saved) else None),
+                    traffic_note="dram__bytes_read.sum + dram__bytes_write.sum of one launch at this shape (ncu --set full, profiles/r02n_render_tc_b*_ncu_summary.txt; "
+                                 "null at shapes that were not captured): the activation planes the forward saved (3.75 KB per sample point) read back once - "
+                                 "the alternative, recomputing the forward per tile, needs no HBM but 19 more GEMM phases per tile and is slower (bench configs[2] runs it)",
                     peak_source=pk["source"] + " bf16 sustained (kernel timed inside the step)",
                     algorithmic_flops_per_launch=pts * FLOP_BWD_PER_POINT, avg_launch_ms=bwd_avg,
                     note="fp32-class products on tcgen05: every operand is a hi/lo bf16 pair and every product 3 MMAs (the 1e-4 "
