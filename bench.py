@@ -576,6 +576,35 @@ def config4_record(a, dev, pk, shapes=8):
     return rec
 
 
+def ray_sampler_record(a, dev, pk, batch=32, H=224, W=224, n=512):
+    """SURVEY §8f-4, the DataLoader's boundary-distance ray sampler (utils/util.py:237-248) for one batch of masks: the GPU transform
+    + device draw next to the CPU transform the reference's workers run per image (vigra is absent: scipy's exact EDT, 1 thread)."""
+    import numpy as np
+    import torch
+    from oracle import sampling_ref
+    from shapeclipper_b200 import sampling
+    g = np.random.RandomState(0)
+    yy, xx = np.mgrid[0:H, 0:W]
+    m = np.stack([((yy - g.randint(60, 160)) ** 2 / float(g.randint(30, 80)) ** 2 + (xx - g.randint(60, 160)) ** 2 / float(g.randint(30, 80)) ** 2 < 1)
+                  for _ in range(batch)]).astype(np.float32)
+    md = torch.from_numpy(m).to(dev)
+    ms_dist = _time_cuda(lambda: sampling.boundary_distance(md), 50)
+    ms_draw = _time_cuda(lambda: sampling.sample_rays(md, n, 3.0), 50)
+    t0 = time.perf_counter()
+    for b in range(8):
+        sampling_ref.boundary_distance_scipy(m[b] > 0.5)
+    cpu_ms = (time.perf_counter() - t0) / 8 * 1e3
+    bytes_alg = batch * H * W * 12.0                       # mask read by both passes + distance written, fp32
+    return dict(workload="ray sampler: %d masks of %dx%d -> boundary distance transform + %d rays per image without replacement" % (batch, H, W, n),
+                launches=2, transform_ms_per_batch=ms_dist, transform_plus_draw_ms_per_batch=ms_draw,
+                cpu_reference=dict(ms_per_image=cpu_ms, cores=1, kind="port",
+                                   note="scipy's exact EDT standing in for vigra.filters.boundaryDistanceTransform (absent), per image as in the DataLoader workers"),
+                speedup_per_image_vs_one_core=cpu_ms * batch / ms_dist,
+                roofline=dict(bound="hbm", unit="GB/s", achieved=bytes_alg / ms_dist / 1e6, peak=pk["hbm_gbs"], frac=bytes_alg / ms_dist / 1e6 / pk["hbm_gbs"],
+                              note="12 B per pixel algorithmic; the column pass does H = 224 integer min-steps per pixel out of L2 (4.5 MB of "
+                                   "uint16 row distances per batch): latency- and ALU-bound at this size, not HBM-bound"))
+
+
 def config0_record():
     """BASELINE configs[0]: one 224 x 224 synthetic image, 32 x 32 rays x 32 samples, CLIP ViT-B/32, one forward + loss + backward
     on the CPU (the reference path itself, no GPU)."""
@@ -635,7 +664,8 @@ def run_ours(a):
         for name, fn in (("configs[0]", config0_record),
                          ("configs[1]", lambda: _config1(a, opt, dev, r)),
                          ("configs[2]", lambda: config2_record(a, dev, pk)),
-                         ("configs[4]", lambda: config4_record(a, dev, pk))):
+                         ("configs[4]", lambda: config4_record(a, dev, pk)),
+                         ("ray_sampler", lambda: ray_sampler_record(a, dev, pk))):
             try:
                 cfgs[name] = fn()
             except Exception as ex:  # noqa: BLE001 - a sub-record never takes the headline line down with it

@@ -11,6 +11,8 @@
  *   sc_clip_encode       CLIP_anno.py:166 clip_model.encode_image (openai/CLIP VisionTransformer)
  *   sc_cosine_topk       CLIP_anno.py:29-57 NN_annotator.calc_matches
  *   sc_render_*          model/renderer.py:57 Renderer.forward, model/implicit.py:163 get_conditional_output
+ *   sc_mc_* / sc_tri_*   utils/eval_3D.py:123-153 (mcubes.marching_cubes, trimesh sample)
+ *   sc_boundary_distance utils/util.py:237-248 compute_sampling_prob (vigra.filters.boundaryDistanceTransform)
  */
 #ifndef SC_B200_H_
 #define SC_B200_H_
@@ -27,7 +29,7 @@ typedef struct CUstream_st* cudaStream_t;
 #endif
 
 /* ABI version of this header; bumped whenever a signature changes. */
-#define SC_B200_ABI_VERSION 3
+#define SC_B200_ABI_VERSION 4
 int sc_abi_version(void);
 
 /* ---- chamfer3D ------------------------------------------------------------
@@ -289,6 +291,19 @@ int sc_mc_emit(const float* level, int batch, int n, float isovalue, const int64
                cudaStream_t stream);
 int sc_tri_area(const float* triangles, int64_t n_tris, float* area, cudaStream_t stream);
 int sc_tri_sample(const float* triangles, const int64_t* face, const float* uv, int64_t count, float* points, cudaStream_t stream);
+
+/* ---- boundary-distance ray sampler (csrc/sampler.cu) ---------------------------------------------
+ * Replaces the CPU leg of utils/util.py:237-248 (compute_sampling_prob, per image in the DataLoader workers, data/pix3d.py:234-239):
+ * vigra.filters.boundaryDistanceTransform(mask > 0.5) and the sampling weights 1 / (distance + uniform_fac).
+ * mask [B, H, W] fp32 device (foreground = mask > threshold); dist [B, H, W] fp32 (or NULL) = Euclidean distance of every pixel
+ * to the nearest pixel of the OTHER class, minus 0.5 (vigra's default InterpixelBoundary); an image without a pixel of the other
+ * class: H + W. keys [B, H, W] (or NULL; needs uniforms [B, H, W] in (0, 1]) = -log(u) (dist + uniform_fac): the n smallest keys of
+ * an image are a sample of n pixels without replacement with probability proportional to 1 / (dist + uniform_fac), i.e. what
+ * np.random.choice(H W, n, p = prob, replace = False) draws (utils/util.py:247). scratch: sc_boundary_distance_scratch_bytes.
+ * Exact (integer d^2, correctly rounded sqrt) for H, W <= 32767 and H^2 + W^2 < 2^24. */
+size_t sc_boundary_distance_scratch_bytes(int batch, int H, int W);
+int sc_boundary_distance(const float* mask, int batch, int H, int W, float threshold, void* scratch, float* dist,
+                         const float* uniforms, float uniform_fac, float* keys, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -7,7 +7,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsc_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 _lib = None
 
 c_float_p = ctypes.c_void_p   # raw device addresses travel as void*
@@ -59,10 +59,11 @@ def _declare(L):
     L.sc_render_losses_pass1.restype = i
     L.sc_render_losses_pass2.argtypes = [vp, vp, vp, vp, vp, vp, i, i, i, f, d, f, vp, vp, vp, vp, vp, vp]
     L.sc_render_losses_pass2.restype = i
-    from . import _render_native, clip, mcubes
+    from . import _render_native, clip, mcubes, sampling
     _render_native.declare(L)
     clip.declare(L)
     mcubes.declare(L)
+    sampling.declare(L)
 
 
 def ptr(t):

@@ -2,10 +2,11 @@
 
     import shapeclipper_b200.shim; shapeclipper_b200.shim.install()
 
-registers `model.renderer`, `model.implicit`, `chamfer_3D`, `clip`, `mcubes` and `trimesh` in sys.modules before the reference
-imports them (model/graph.py:10-12, utils/eval_3D.py:4-6, CLIP_anno.py:7). The three third-party names are only registered when
+registers `model.renderer`, `model.implicit`, `chamfer_3D`, `clip`, `mcubes`, `trimesh` and `vigra` in sys.modules before the reference
+imports them (model/graph.py:10-12, utils/eval_3D.py:4-6, CLIP_anno.py:7, utils/util.py:10). The third-party names are only registered when
 the real packages are not importable (or are empty test stubs): the reference's annotator then gets this package's image tower
-(`clip.load(name, device)` -> (model, preprocess)) and its evaluation this package's GPU marching cubes / surface sampler."""
+(`clip.load(name, device)` -> (model, preprocess)), its evaluation this package's GPU marching cubes / surface sampler and its
+DataLoader's ray sampler (utils/util.py:237-248) this package's boundary-distance transform."""
 import sys
 
 
@@ -31,4 +32,8 @@ def install():
         from . import mcubes
         sys.modules["mcubes"] = mcubes
         sys.modules["trimesh"] = mcubes
+    if absent("vigra"):                              # utils/util.py:243 vigra.filters.boundaryDistanceTransform
+        from . import sampling
+        sys.modules["vigra"] = sampling.vigra
+        sys.modules["vigra.filters"] = sampling.vigra.filters
     return renderer, implicit, chamfer_3D
