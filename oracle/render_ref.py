@@ -19,7 +19,7 @@ What is restated (reference file:line, relative to /root/reference):
 
 Parity pinning: the reference has no tests or golden vectors. This restatement is
 pinned against the reference itself, imported unmodified in the build container
-(tests/test_oracle_vs_reference.py) and against fixtures that import produced
+(tests/test_oracle_render.py) and against fixtures that import produced
 (tests/golden/*.pt, generator tests/gen_golden.py).
 
 Everything is dtype-generic: run it in float32 to mirror the reference, in float64 for a truth run.
