@@ -665,7 +665,8 @@ def run_ours(a):
                          ("configs[1]", lambda: _config1(a, opt, dev, r)),
                          ("configs[2]", lambda: config2_record(a, dev, pk)),
                          ("configs[4]", lambda: config4_record(a, dev, pk)),
-                         ("ray_sampler", lambda: ray_sampler_record(a, dev, pk))):
+                         ("ray_sampler", lambda: ray_sampler_record(a, dev, pk)),
+                         ("step_with_clip_fp16", lambda: _step_clip_fp16(a, opt, dev))):
             try:
                 cfgs[name] = fn()
             except Exception as ex:  # noqa: BLE001 - a sub-record never takes the headline line down with it
@@ -683,6 +684,23 @@ def _config1(a, opt, dev, main):
     r = measure_train_step(a, opt, 16, steps=min(a.steps, 20), warmup=3, rank=0, world=1, dev=dev, sample_clocks=False)
     return dict(workload=workload_config(16, 1, opt, clip=r["clip"])["workload"], images_per_s=r["value"], ms_per_step=r["ms_per_step"],
                 e2e=r["e2e"], gpu_launches=r["gpu_launches"], roofline=r["roofline"])
+
+
+def _step_clip_fp16(a, opt, dev):
+    """The headline step with the CLIP leg in the tower's fp16-operand mode: the arithmetic the reference itself runs CLIP at on CUDA
+    (`clip.load` returns an fp16 model, CLIP_anno.py:16; here with fp32 accumulation and an fp32 residual stream, 2.7e-4 on the
+    embedding). The headline keeps the fp32-class parity mode (hi/lo bf16 pairs, 3 MMAs per product, 1e-4)."""
+    old = os.environ.get("SC_BENCH_CLIP")
+    os.environ["SC_BENCH_CLIP"] = "fp16"
+    try:
+        r = measure_train_step(a, opt, a.batch, steps=min(a.steps, 20), warmup=3, rank=0, world=1, dev=dev, sample_clocks=False)
+    finally:
+        if old is None:
+            os.environ.pop("SC_BENCH_CLIP", None)
+        else:
+            os.environ["SC_BENCH_CLIP"] = old
+    return dict(workload=workload_config(a.batch, 1, opt, clip=r["clip"])["workload"] + "; CLIP leg in fp16 operands (the reference's own CLIP precision)",
+                images_per_s=r["value"], ms_per_step=r["ms_per_step"], e2e_images_per_s=r["e2e"]["value"])
 
 
 def main():
