@@ -327,10 +327,12 @@ def test_fused_eikonal_points_match_torch_restatement():
         _close(a, b, name, 2e-6)
 
 
-@pytest.mark.parametrize("S", [16, 32])
+@pytest.mark.parametrize("S", [4, 8, 16, 32, 128])
 def test_other_sample_counts_forward_and_backward_vs_oracle(S):
-    """render.n_samples_uniform = 16 / 32 (several rays per 128-point tile, segmented scans inside one warp): forward outputs and
-    a few gradients against the oracle's CPU autograd. Tolerances as in smoke(): outputs 1e-4, gradients 2e-3 of the largest entry."""
+    """render.n_samples_uniform = 4 ... 32 (several rays per 128-point tile, segmented scans inside one warp; the backward's ray group
+    takes them as two half tiles of 64 points) and 128 (one ray spans the tile: the backward runs without its ray group and recomputes
+    the forward): forward outputs and a few gradients against the oracle's CPU autograd. Tolerances as in smoke(): outputs 1e-4,
+    gradients 2e-3 of the largest entry."""
     from shapeclipper_b200 import options
     from shapeclipper_b200.implicit import SDFNetwork, RGBNetwork
     from shapeclipper_b200.renderer import Renderer
