@@ -9,7 +9,7 @@
 // HBM-bound integer work, exact and separable: d^2(y, x) = min over rows y' of (y - y')^2 + h(y', x)^2, where h(y', x) is the distance
 // ALONG row y' from column x to the nearest pixel of the other class. Pass 1 (one warp per row, two warp max/min scans) writes both
 // row-distance planes (to the nearest foreground / background pixel) as uint16; pass 2 (one thread per pixel, coalesced over x) takes
-// the column minimum in integers, so the result is the correctly rounded sqrt of an exact integer: bit-equal to the oracle.
+// the column minimum in integers (rows visited outward from the pixel's own row, stopping where no farther row can win), so the result is the correctly rounded sqrt of an exact integer: bit-equal to the oracle.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -83,11 +83,22 @@ __global__ void edt_cols_kernel(const float* __restrict__ mask, int B, int H, in
     const size_t img = i / ((size_t)W * H);
     const bool fg = mask[i] > thr;
     const uint16_t* plane = (fg ? row_b : row_f) + img * (size_t)H * W + x;
+    // rows outward from y: once dy^2 reaches the best squared distance no farther row can improve it (boundaries are near for most
+    // pixels: ~10x fewer steps than the full column; neighbouring pixels stop at similar dy, so warps stay converged)
     unsigned best = 0xFFFFFFFFu;
-    for (int yy = 0; yy < H; ++yy) {
-        const unsigned h = plane[(size_t)yy * W];
-        const unsigned dy = (unsigned)(yy > y ? yy - y : y - yy);
-        if (h != kNone && dy * dy < best) best = min(best, dy * dy + h * h);
+    const int dmax = max(y, H - 1 - y);
+    for (int d0 = 0; d0 <= dmax; d0 += 8) {                  // 8 rows each way per step: 16 independent loads, one exit test
+        if ((unsigned)(d0 * d0) >= best) break;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int dy = d0 + j;
+            const unsigned dy2 = (unsigned)(dy * dy);
+            const int ya = y - dy, yb = y + dy;
+            const unsigned ha = (ya >= 0) ? plane[(size_t)ya * W] : kNone;
+            const unsigned hb = (yb < H) ? plane[(size_t)yb * W] : kNone;
+            if (ha != kNone) best = min(best, dy2 + ha * ha);
+            if (hb != kNone) best = min(best, dy2 + hb * hb);
+        }
     }
     const float d = (best == 0xFFFFFFFFu) ? (float)(H + W) : __fsub_rn(__fsqrt_rn((float)best), 0.5f);
     if (dist != nullptr) dist[i] = d;
