@@ -300,7 +300,7 @@ int sc_tri_sample(const float* triangles, const int64_t* face, const float* uv, 
  * class: H + W. keys [B, H, W] (or NULL; needs uniforms [B, H, W] in (0, 1]) = -log(u) (dist + uniform_fac): the n smallest keys of
  * an image are a sample of n pixels without replacement with probability proportional to 1 / (dist + uniform_fac), i.e. what
  * np.random.choice(H W, n, p = prob, replace = False) draws (utils/util.py:247). scratch: sc_boundary_distance_scratch_bytes.
- * Exact (integer d^2, correctly rounded sqrt) for H, W <= 32767 and H^2 + W^2 < 2^24. */
+ * H, W <= 23170; exact (integer d^2, correctly rounded sqrt) while H^2 + W^2 < 2^24. */
 size_t sc_boundary_distance_scratch_bytes(int batch, int H, int W);
 int sc_boundary_distance(const float* mask, int batch, int H, int W, float threshold, void* scratch, float* dist,
                          const float* uniforms, float uniform_fac, float* keys, cudaStream_t stream);

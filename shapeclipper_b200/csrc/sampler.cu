@@ -8,7 +8,7 @@
 //
 // HBM-bound integer work, exact and separable: d^2(y, x) = min over rows y' of (y - y')^2 + h(y', x)^2, where h(y', x) is the distance
 // ALONG row y' from column x to the nearest pixel of the other class. Pass 1 (one warp per row, two warp max/min scans) writes both
-// row-distance planes (to the nearest foreground / background pixel) as uint16; pass 2 (one thread per pixel, coalesced over x) takes
+// squared row-distance planes (to the nearest foreground / background pixel) as uint32; pass 2 (one thread per pixel, coalesced over x) takes
 // the column minimum in integers (rows visited outward from the pixel's own row, stopping where no farther row can win), so the result is the correctly rounded sqrt of an exact integer: bit-equal to the oracle.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,17 +17,17 @@
 
 namespace scsamp {
 
-constexpr unsigned kNone = 0xFFFFu;
+constexpr unsigned kNone = 0x3FFFFFFFu;      // "no such pixel in this row": a squared distance no sum with dy^2 < 2^30 can beat
 
-// pass 1: row b*H + y. out_f / out_b [B, H, W] uint16: distance along the row to the nearest pixel with mask > thr / <= thr
-__global__ void edt_rows_kernel(const float* __restrict__ mask, int rows, int W, float thr, uint16_t* __restrict__ out_f,
-                                uint16_t* __restrict__ out_b)
+// pass 1: row b*H + y. out_f / out_b [B, H, W] uint32: SQUARED distance along the row to the nearest pixel with mask > thr / <= thr
+__global__ void edt_rows_kernel(const float* __restrict__ mask, int rows, int W, float thr, uint32_t* __restrict__ out_f,
+                                uint32_t* __restrict__ out_b)
 {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     const float* m = mask + (size_t)row * W;
-    uint16_t* of = out_f + (size_t)row * W;
-    uint16_t* ob = out_b + (size_t)row * W;
+    uint32_t* of = out_f + (size_t)row * W;
+    uint32_t* ob = out_b + (size_t)row * W;
     // left to right: index of the last foreground / background pixel at or before x
     int carry_f = -1, carry_b = -1;
     for (int x0 = 0; x0 < W; x0 += 32) {
@@ -42,8 +42,8 @@ __global__ void edt_rows_kernel(const float* __restrict__ mask, int rows, int W,
         }
         lf = max(lf, carry_f); lb = max(lb, carry_b);
         if (in) {
-            of[x] = (uint16_t)(lf >= 0 ? (unsigned)(x - lf) : kNone);
-            ob[x] = (uint16_t)(lb >= 0 ? (unsigned)(x - lb) : kNone);
+            of[x] = lf >= 0 ? (unsigned)((x - lf) * (x - lf)) : kNone;
+            ob[x] = lb >= 0 ? (unsigned)((x - lb) * (x - lb)) : kNone;
         }
         carry_f = __shfl_sync(0xffffffffu, lf, 31); carry_b = __shfl_sync(0xffffffffu, lb, 31);
     }
@@ -62,8 +62,8 @@ __global__ void edt_rows_kernel(const float* __restrict__ mask, int rows, int W,
         }
         nf = min(nf, carry_f); nb = min(nb, carry_b);
         if (in) {
-            if (nf < big) of[x] = (uint16_t)min((unsigned)of[x], (unsigned)(nf - x));
-            if (nb < big) ob[x] = (uint16_t)min((unsigned)ob[x], (unsigned)(nb - x));
+            if (nf < big) of[x] = min(of[x], (unsigned)((nf - x) * (nf - x)));
+            if (nb < big) ob[x] = min(ob[x], (unsigned)((nb - x) * (nb - x)));
         }
         carry_f = __shfl_sync(0xffffffffu, nf, 0); carry_b = __shfl_sync(0xffffffffu, nb, 0);
     }
@@ -72,8 +72,8 @@ __global__ void edt_rows_kernel(const float* __restrict__ mask, int rows, int W,
 // pass 2: one thread per pixel. dist = sqrt(min_y' (y - y')^2 + h^2) - 0.5, h from the plane of the OTHER class; an image without
 // a pixel of the other class has no boundary: dist = H + W. keys (optional) = -log(u) * (dist + fac): the exponential race whose
 // n smallest keys are a sample of n pixels WITHOUT replacement with probabilities proportional to 1 / (dist + fac).
-__global__ void edt_cols_kernel(const float* __restrict__ mask, int B, int H, int W, float thr, const uint16_t* __restrict__ row_f,
-                                const uint16_t* __restrict__ row_b, float* __restrict__ dist, const float* __restrict__ uniforms,
+__global__ void edt_cols_kernel(const float* __restrict__ mask, int B, int H, int W, float thr, const uint32_t* __restrict__ row_f,
+                                const uint32_t* __restrict__ row_b, float* __restrict__ dist, const float* __restrict__ uniforms,
                                 float fac, float* __restrict__ keys)
 {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,7 +82,7 @@ __global__ void edt_cols_kernel(const float* __restrict__ mask, int B, int H, in
     const int x = (int)(i % W), y = (int)((i / W) % H);
     const size_t img = i / ((size_t)W * H);
     const bool fg = mask[i] > thr;
-    const uint16_t* plane = (fg ? row_b : row_f) + img * (size_t)H * W + x;
+    const uint32_t* plane = (fg ? row_b : row_f) + img * (size_t)H * W + x;
     // rows outward from y: once dy^2 reaches the best squared distance no farther row can improve it (boundaries are near for most
     // pixels: ~10x fewer steps than the full column; neighbouring pixels stop at similar dy, so warps stay converged)
     unsigned best = 0xFFFFFFFFu;
@@ -94,13 +94,12 @@ __global__ void edt_cols_kernel(const float* __restrict__ mask, int B, int H, in
             const int dy = d0 + j;
             const unsigned dy2 = (unsigned)(dy * dy);
             const int ya = y - dy, yb = y + dy;
-            const unsigned ha = (ya >= 0) ? plane[(size_t)ya * W] : kNone;
+            const unsigned ha = (ya >= 0) ? plane[(size_t)ya * W] : kNone;      // squared row distances; kNone never wins
             const unsigned hb = (yb < H) ? plane[(size_t)yb * W] : kNone;
-            if (ha != kNone) best = min(best, dy2 + ha * ha);
-            if (hb != kNone) best = min(best, dy2 + hb * hb);
+            best = min(best, dy2 + min(ha, hb));
         }
     }
-    const float d = (best == 0xFFFFFFFFu) ? (float)(H + W) : __fsub_rn(__fsqrt_rn((float)best), 0.5f);
+    const float d = (best >= kNone) ? (float)(H + W) : __fsub_rn(__fsqrt_rn((float)best), 0.5f);
     if (dist != nullptr) dist[i] = d;
     if (keys != nullptr) {
         const float u = fmaxf(uniforms[i], 1.17549435e-38f);
@@ -112,7 +111,7 @@ __global__ void edt_cols_kernel(const float* __restrict__ mask, int B, int H, in
 
 extern "C" size_t sc_boundary_distance_scratch_bytes(int batch, int H, int W) {
     if (batch <= 0 || H <= 0 || W <= 0) return 0;
-    return (size_t)2 * batch * H * W * sizeof(uint16_t);
+    return (size_t)2 * batch * H * W * sizeof(uint32_t);
 }
 
 extern "C" int sc_boundary_distance(const float* mask, int batch, int H, int W, float threshold, void* scratch, float* dist,
@@ -120,10 +119,10 @@ extern "C" int sc_boundary_distance(const float* mask, int batch, int H, int W, 
 {
     if (mask == nullptr || scratch == nullptr || (dist == nullptr && keys == nullptr) || (keys != nullptr && uniforms == nullptr))
         return (int)cudaErrorInvalidValue;
-    if (H <= 0 || W <= 0 || H > 32767 || W > 32767) return (int)cudaErrorInvalidValue;      // uint16 row distances, 32-bit d^2
+    if (H <= 0 || W <= 0 || H > 23170 || W > 23170) return (int)cudaErrorInvalidValue;      // 32-bit d^2 = dy^2 + dx^2 < 2^30
     if (batch <= 0) return 0;
-    uint16_t* row_f = reinterpret_cast<uint16_t*>(scratch);
-    uint16_t* row_b = row_f + (size_t)batch * H * W;
+    uint32_t* row_f = reinterpret_cast<uint32_t*>(scratch);
+    uint32_t* row_b = row_f + (size_t)batch * H * W;
     const int rows = batch * H, warps = 8;
     scsamp::edt_rows_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, stream>>>(mask, rows, W, threshold, row_f, row_b);
     const size_t n = (size_t)batch * H * W;
