@@ -404,7 +404,9 @@ def measure_train_step(a, opt, batch_size, steps, warmup, rank, world, dev, clip
     pts = batch_size * R * S                                    # sample points per render launch
     bwd_ms, bwd_n = kernel_ms.get("render_bwd", (0.0, 1))
     fwd_ms, fwd_n = kernel_ms.get("render_fwd", (0.0, 1))
-    bwd_avg, fwd_avg = bwd_ms / max(bwd_n, 1), fwd_ms / max(fwd_n, 1)
+    refwd_ms, refwd_n = kernel_ms.get("render_fwd_for_backward", (0.0, 0))      # chunked backward: the forward run again per chunk
+    # per RENDER (one forward launch each); a chunked backward is several launches per render: their sum
+    bwd_avg, fwd_avg = bwd_ms / max(fwd_n, 1), fwd_ms / max(fwd_n, 1)
     ffma_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
     achieved = pts * FLOP_BWD_PER_POINT / (bwd_avg * 1e-3) / 1e12 if bwd_avg > 0 else 0.0
     share = lambda ms: ms / span_steps / ms_step
@@ -417,14 +419,19 @@ def measure_train_step(a, opt, batch_size, steps, warmup, rank, world, dev, clip
                                  "the alternative, recomputing the forward per tile, needs no HBM but 19 more GEMM phases per tile and is slower (bench configs[2] runs it)",
                     peak_source=pk["source"] + " bf16 sustained (kernel timed inside the step)",
                     algorithmic_flops_per_launch=pts * FLOP_BWD_PER_POINT, avg_launch_ms=bwd_avg,
+                    launches_per_render=bwd_n / max(fwd_n, 1),
                     note="fp32-class products on tcgen05: every operand is a hi/lo bf16 pair and every product 3 MMAs (the 1e-4 "
                          "parity target rules out plain bf16/tf32 operands, BASELINE.md §2), so this scheme tops out at 1/3 of "
                          "the bf16 peak; flops follow SURVEY.md §8d's convention (2*MAC of the GEMMs as the reference runs them)",
                     timing="CUDA events around the kernel on its launch stream" + ("" if a.eager else
                            " (external event nodes inside the step's CUDA graph; 6 replays)"),
                     fp32_ffma_peak_tflops=ffma_peak, frac_of_fp32_ffma=achieved / ffma_peak,
-                    backward_mode="saved activations" if saved else "recompute (saved planes would not fit)",
-                    share_of_step=dict(render_bwd=share(bwd_ms), render_fwd=share(fwd_ms),
+                    backward_mode=("saved activations" if saved else
+                                   ("chunked: per %d images the forward again with the saved-activation buffer (%.1f ms per render, not in "
+                                    "avg_launch_ms) + the saved-activation backward; %d backward launches per render"
+                                    % (max(1, round(batch_size * fwd_n / max(bwd_n, 1))), refwd_ms / max(fwd_n, 1), round(bwd_n / max(fwd_n, 1))))
+                                   if refwd_n else "recompute per tile (saved planes would not fit)"),
+                    share_of_step=dict(render_bwd=share(bwd_ms), render_fwd=share(fwd_ms), render_fwd_for_backward=share(refwd_ms),
                                        **{k: share(v[0]) for k, v in kernel_ms.items() if k.startswith("sdf") or k.startswith("clip")}),
                     share_note=("clip_encode runs on a forked low-priority stream and fills the SMs the small kernels between the render "
                                 "launches leave idle: its share is the span it is spread over, not exclusive time") if (clip and not a.no_side_stream) else None,
@@ -464,7 +471,8 @@ def _time_cuda(fn, iters, warm=3):
 def config2_record(a, dev, pk):
     """BASELINE configs[2]: batch 64 — CLIP ViT-B/32 encode + cosine top-6 (k_nearest = 5 after dropping self) in every precision
     mode the encoder has, and the two-render 128 x 128 TRAINING step (full-grid rays: 67 108 864 sample points per render; the
-    backward recomputes, the saved planes would be 252 GB)."""
+    saved planes of a whole render would be 252 GB, so the backward walks the batch in chunks of images: forward again with the
+    saved-activation buffer, then the saved-activation backward; SC_RENDER_CHUNKED_BACKWARD=0 selects the per-tile recompute kernel)."""
     import torch
     from shapeclipper_b200 import clip as scclip, options
     rec = {}

@@ -197,6 +197,17 @@ def saved_buffer(device, batch, n_per_image, n_samples):
         return None                                    # the backward recomputes the forward per tile instead
 
 
+def saved_chunk_images(device, batch, n_per_image, n_samples):
+    """How many images' saved activations fit the budget of saved_buffer() at once (0: not even one; >= batch: all of them)."""
+    per_image = _lib.lib().sc_render_tc_saved_bytes(1, int(n_per_image), int(n_samples))
+    if per_image == 0:
+        return 0
+    free, _ = torch.cuda.mem_get_info(device)
+    reusable = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    cap = min(SAVE_ACTIVATIONS_MAX_BYTES, (free + reusable) // 2)
+    return int(min(batch, cap // per_image))
+
+
 def saved_buffer_bytes(batch, n_per_image, n_samples):
     """Bytes of saved activations one training render of this shape would keep for its backward (0 = the backward recomputes)."""
     n = _lib.lib().sc_render_tc_saved_bytes(int(batch), int(n_per_image), int(n_samples))
@@ -268,11 +279,11 @@ def _entry(L, direction, tc, args):
     return getattr(L, name), name
 
 
-def launch_forward(args, device, tc=False):
+def launch_forward(args, device, tc=False, span=None):
     L = _lib.lib()
     with torch.cuda.device(device):
         stream = ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        with TIMERS.span("render_fwd" if args.mode == 0 else "sdf_query_fwd", device):
+        with TIMERS.span(span or ("render_fwd" if args.mode == 0 else "sdf_query_fwd"), device):
             fn, name = _entry(L, "forward", tc, args)
             _lib.check(fn(ctypes.byref(args), stream), name)
     TIMERS.count()

@@ -21,6 +21,13 @@ STEP_PRECISIONS = ("tc", "bf16")   # render arithmetic modes bench.py's configs[
 
 
 SAVE_ACTIVATIONS = _os.environ.get("SC_RENDER_SAVE_ACTIVATIONS", "1") != "0"
+# A render too large to keep its activations (3.75 KB per sample point; e.g. 128 x 128 rays x 64 images = 252 GB): the backward walks
+# the batch in chunks of images — forward again WITH the saved buffer for the chunk, then the saved-activation backward on it —
+# instead of the kernel that recomputes the forward per tile (1.3 + 2.6 ns per sample point against 5.4).
+CHUNKED_BACKWARD = _os.environ.get("SC_RENDER_CHUNKED_BACKWARD", "1") != "0"
+# > 0: never keep a whole render's activations; the backward always walks chunks of this many images (bounds the memory of a
+# training render to chunk x 3.75 KB x sample points per image; also how the tests reach the chunked path at small sizes)
+CHUNK_IMAGES = int(_os.environ.get("SC_RENDER_CHUNK_IMAGES", "0"))
 
 
 def set_precision(forward=None, backward=None):
@@ -150,7 +157,7 @@ class _RenderFn(torch.autograd.Function):
         # generation-1 tensor-core kernels, some input needs a gradient: the forward saves its per-point activations
         # (3.75 KB per sample point) and the backward reads them back instead of recomputing 19 of its 45 GEMM phases
         saved = None
-        if tc == "tc" and _bwd_tc() == "tc" and SAVE_ACTIVATIONS and any(ctx.needs_input_grad):
+        if tc == "tc" and _bwd_tc() == "tc" and SAVE_ACTIVATIONS and any(ctx.needs_input_grad) and not (CHUNK_IMAGES > 0 and CHUNKED_BACKWARD):
             saved = rn.saved_buffer(dev, B, R, cfg["n_samples"])
             if saved is not None:
                 args.saved = ctypes.c_void_p(saved.data_ptr())
@@ -199,6 +206,14 @@ class _RenderFn(torch.autograd.Function):
         for name, t in (("rgb_bar", rgb_bar), ("mask_bar", mask_bar), ("depth_bar", depth_bar), ("normal_bar", normal_bar)):
             if t is not None:
                 setattr(args, name, ctypes.c_void_p(t.data_ptr()))
+        S = cfg["n_samples"]
+        n_img = 0
+        if (ctx.saved_acts is None and tc == "tc" and _fwd_tc() == "tc" and SAVE_ACTIVATIONS and CHUNKED_BACKWARD and S <= 64
+                and _single("forward") == _single("backward")):
+            n_img = min(CHUNK_IMAGES, B) if CHUNK_IMAGES > 0 else rn.saved_chunk_images(dev, B, R, S)
+        if n_img >= 1 and (B > 1 or CHUNK_IMAGES > 0):
+            return _RenderFn._backward_chunked(ctx, L, args, n_img, (rgb_bar, mask_bar, depth_bar, normal_bar),
+                                               (cb_bar, dirs_bar, fac_bar, loc_bar, sd_bar), partial, n_ctas)
         if ctx.saved_acts is not None and tc == "tc":
             args.saved = ctypes.c_void_p(ctx.saved_acts.data_ptr())
         rn.launch_backward(args, dev, tc=tc)
@@ -206,6 +221,71 @@ class _RenderFn(torch.autograd.Function):
         gw, gb, z_sdf_bar, z_rgb_bar, beta_bar = _finalize(L, partial, n_ctas, cb_bar, z_sdf, z_rgb, blob, B, ws, bs, True)
         beta_param_bar = (beta_bar * torch.sign(beta_c)).reshape(())
         return (None, beta_param_bar, loc_bar, dirs_bar, fac_bar, sd_bar, z_sdf_bar, z_rgb_bar, None, None, *gw, *gb)
+
+    @staticmethod
+    def _backward_chunked(ctx, L, args, n_img, ups, outs, partial, n_ctas):
+        """The backward of a render whose activations did not fit: per chunk of n_img images, the forward kernel again with the
+        saved-activation buffer (outputs discarded: same inputs, same jitter => same planes), the saved-activation backward kernel,
+        and one finalize that adds the chunk's parameter gradients to the running sums."""
+        saved = ctx.saved_tensors
+        blob, cb, beta_c, cam_loc, ray_dirs, depth_fac, scale_dist, t_vals, jit, z_sdf, z_rgb = saved[:11]
+        params = saved[11:]
+        ws, bs = list(params[:10]), list(params[10:])
+        cfg = ctx.cfg
+        dev = ray_dirs.device
+        B, R, S = ray_dirs.shape[0], ray_dirs.shape[1], cfg["n_samples"]
+        cb_bar, dirs_bar, fac_bar, loc_bar, sd_bar = outs
+        buf = rn.saved_buffer(dev, n_img, R, S)
+        if buf is None:
+            raise RuntimeError("saved-activation chunk buffer could not be allocated")
+        dummy = [torch.empty(n_img, R, c, device=dev) for c in (3, 1, 1, 1, 3)]         # rgb mask mask_hard depth normal of a chunk
+        fscratch = rn.scratch(dev, backward=False, tc="tc")
+        kblob = rn.packed_tc_blob(ws, bs, blob)
+        addr = lambda t, off: ctypes.c_void_p(t.data_ptr() + 4 * int(off))
+        gw_sum = gb_sum = None
+        z_sdf_bar = torch.empty(B, 64, device=dev)
+        z_rgb_bar = torch.empty(B, 64, device=dev)
+        beta_sum = torch.zeros(1, device=dev)
+        for b0 in range(0, B, n_img):
+            nb = min(n_img, B - b0)
+            fa = _new_args(mode=0, batch=nb, n_per_image=R, n_samples=S, beta_min=cfg["beta_min"], cam_dist=cfg["cam_dist"],
+                           half_range=cfg["half_range"], bg_color=cfg["bg_color"], normal_pow=cfg["normal_pow"], blob=kblob,
+                           beta_param=beta_c, t_vals=t_vals, rgb=dummy[0], mask=dummy[1], mask_hard=dummy[2], depth=dummy[3],
+                           normal=dummy[4], scratch=fscratch, saved=buf, precision=_single("forward"))
+            fa.cb = addr(cb, b0 * 256); fa.cam_loc = addr(cam_loc, b0 * 3); fa.ray_dirs = addr(ray_dirs, b0 * R * 3)
+            fa.depth_fac = addr(depth_fac, b0 * R); fa.scale_dist = addr(scale_dist, b0)
+            if ctx.has_jitter:
+                fa.jitter = addr(jit, b0 * R * S)
+            rn.launch_forward(fa, dev, tc="tc", span="render_fwd_for_backward")
+            ba = _new_args(mode=0, batch=nb, n_per_image=R, n_samples=S, beta_min=cfg["beta_min"], cam_dist=cfg["cam_dist"],
+                           half_range=cfg["half_range"], bg_color=cfg["bg_color"], normal_pow=cfg["normal_pow"], blob=kblob,
+                           beta_param=beta_c, t_vals=t_vals, grad_partial=partial, scratch=args.scratch, saved=buf,
+                           precision=_single("backward"))
+            ba.cb = fa.cb; ba.cam_loc = fa.cam_loc; ba.ray_dirs = fa.ray_dirs; ba.depth_fac = fa.depth_fac; ba.scale_dist = fa.scale_dist
+            if ctx.has_jitter:
+                ba.jitter = fa.jitter
+            for name, t, w in (("rgb_bar", ups[0], 3), ("mask_bar", ups[1], 1), ("depth_bar", ups[2], 1), ("normal_bar", ups[3], 3)):
+                if t is not None:
+                    setattr(ba, name, addr(t, b0 * R * w))
+            ba.cb_bar = addr(cb_bar, b0 * 448); ba.ray_dirs_bar = addr(dirs_bar, b0 * R * 3); ba.depth_fac_bar = addr(fac_bar, b0 * R)
+            ba.cam_loc_bar = addr(loc_bar, b0 * 3); ba.scale_dist_bar = addr(sd_bar, b0)
+            rn.launch_backward(ba, dev, tc="tc")
+            gw, gb, zs, zr, beta_bar = _finalize(L, partial, n_ctas, cb_bar[b0:b0 + nb], z_sdf[b0:b0 + nb], z_rgb[b0:b0 + nb], blob, nb,
+                                                 ws, bs, True)
+            z_sdf_bar[b0:b0 + nb] = zs
+            z_rgb_bar[b0:b0 + nb] = zr
+            beta_sum += beta_bar
+            if gw[0] is not None:                                   # not fused into .grad: sum the chunks here
+                if gw_sum is None:
+                    gw_sum, gb_sum = list(gw), list(gb)
+                else:
+                    for i in range(10):
+                        if gw[i] is not None:
+                            gw_sum[i] += gw[i]; gb_sum[i] += gb[i]
+        if gw_sum is None:
+            gw_sum, gb_sum = [None] * 10, [None] * 10
+        beta_param_bar = (beta_sum * torch.sign(beta_c)).reshape(())
+        return (None, beta_param_bar, loc_bar, dirs_bar, fac_bar, sd_bar, z_sdf_bar, z_rgb_bar, None, None, *gw_sum, *gb_sum)
 
 
 class _SDFQueryFn(torch.autograd.Function):

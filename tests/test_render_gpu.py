@@ -11,18 +11,22 @@ from oracle import render_ref as R
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["tc", "tc-recompute", "tc2", "fp32"])
+@pytest.fixture(autouse=True, params=["tc", "tc-recompute", "tc-chunked", "tc2", "fp32"])
 def render_precision(request):
     """Every test runs on all generations of the render kernels: "tc2" (tcgen05 tensor cores on hi/lo bf16 operand pairs, two
-    64-point tile chains per CTA; selectable), "tc" (one 128-point tile per CTA; the default; with and without saved activations) and "fp32" (FP32 FFMA)."""
+    64-point tile chains per CTA; selectable), "tc" (one 128-point tile per CTA; the default; with saved activations, with the
+    per-tile recompute backward, and with the chunked backward — forward again + saved-activation backward, one image at a time —
+    that renders too large to keep their activations take) and "fp32" (FP32 FFMA)."""
     from shapeclipper_b200 import render_fn
-    old, old_save = dict(render_fn.PRECISION), render_fn.SAVE_ACTIVATIONS
+    old, old_save, old_chunk = dict(render_fn.PRECISION), render_fn.SAVE_ACTIVATIONS, render_fn.CHUNK_IMAGES
     mode = request.param.split("-")[0]
     render_fn.SAVE_ACTIVATIONS = request.param != "tc-recompute"     # "tc": the backward reads the forward's saved activations
+    render_fn.CHUNK_IMAGES = 1 if request.param == "tc-chunked" else 0
     render_fn.set_precision(forward=mode, backward=mode)
     yield request.param
     render_fn.set_precision(forward=old["forward"], backward=old["backward"])
     render_fn.SAVE_ACTIVATIONS = old_save
+    render_fn.CHUNK_IMAGES = old_chunk
 REL = 1e-4
 # Unit normals of grazing rays are ill-conditioned: on the golden fixtures the reference's own fp32 result is 1.8e-4
 # (mask 2e-3) to 1.8e-3 (mask 1e-4) away from an fp64 evaluation of the same inputs (measured with
