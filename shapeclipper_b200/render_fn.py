@@ -211,8 +211,9 @@ class _RenderFn(torch.autograd.Function):
         if (ctx.saved_acts is None and tc == "tc" and _fwd_tc() == "tc" and SAVE_ACTIVATIONS and CHUNKED_BACKWARD and S <= 64
                 and _single("forward") == _single("backward")):
             n_img = min(CHUNK_IMAGES, B) if CHUNK_IMAGES > 0 else rn.saved_chunk_images(dev, B, R, S)
-        if n_img >= 1 and (B > 1 or CHUNK_IMAGES > 0):
-            return _RenderFn._backward_chunked(ctx, L, args, n_img, (rgb_bar, mask_bar, depth_bar, normal_bar),
+        buf = rn.saved_buffer(dev, n_img, R, S) if (n_img >= 1 and (B > 1 or CHUNK_IMAGES > 0)) else None
+        if buf is not None:                        # (None: no memory for even one chunk -> the per-tile recompute kernel below)
+            return _RenderFn._backward_chunked(ctx, L, args, n_img, buf, (rgb_bar, mask_bar, depth_bar, normal_bar),
                                                (cb_bar, dirs_bar, fac_bar, loc_bar, sd_bar), partial, n_ctas)
         if ctx.saved_acts is not None and tc == "tc":
             args.saved = ctypes.c_void_p(ctx.saved_acts.data_ptr())
@@ -223,7 +224,7 @@ class _RenderFn(torch.autograd.Function):
         return (None, beta_param_bar, loc_bar, dirs_bar, fac_bar, sd_bar, z_sdf_bar, z_rgb_bar, None, None, *gw, *gb)
 
     @staticmethod
-    def _backward_chunked(ctx, L, args, n_img, ups, outs, partial, n_ctas):
+    def _backward_chunked(ctx, L, args, n_img, buf, ups, outs, partial, n_ctas):
         """The backward of a render whose activations did not fit: per chunk of n_img images, the forward kernel again with the
         saved-activation buffer (outputs discarded: same inputs, same jitter => same planes), the saved-activation backward kernel,
         and one finalize that adds the chunk's parameter gradients to the running sums."""
@@ -235,9 +236,6 @@ class _RenderFn(torch.autograd.Function):
         dev = ray_dirs.device
         B, R, S = ray_dirs.shape[0], ray_dirs.shape[1], cfg["n_samples"]
         cb_bar, dirs_bar, fac_bar, loc_bar, sd_bar = outs
-        buf = rn.saved_buffer(dev, n_img, R, S)
-        if buf is None:
-            raise RuntimeError("saved-activation chunk buffer could not be allocated")
         dummy = [torch.empty(n_img, R, c, device=dev) for c in (3, 1, 1, 1, 3)]         # rgb mask mask_hard depth normal of a chunk
         fscratch = rn.scratch(dev, backward=False, tc="tc")
         kblob = rn.packed_tc_blob(ws, bs, blob)
